@@ -1,0 +1,162 @@
+/*
+ * slammatch.h -- C-ABI of libslammatch.so: exact brute-force Hamming 2-nearest-neighbour matching of
+ * 256-bit ORB descriptors on NVIDIA B200 (sm_100a), with the Lowe ratio test and cross-check.
+ *
+ * This is the drop-in boundary for ONE path of the reference pipeline (DavidHan008/SLAM-1, a Python
+ * program; file:line below are relative to its tree).  The reference has no FFI of its own: it calls
+ * OpenCV's DescriptorMatcher through the cv2 Python binding.  Each entry point cites the reference
+ * interface it replaces; INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ *   reference today                                        replaced by
+ *   -----------------------------------------------------  ---------------------------------------------
+ *   cv2.FlannBasedMatcher(indexParams, searchParams)       slm_create / slm_destroy  (one ctx per thread+GPU,
+ *     tracking.py:14-17  keypoint.py:40-43  Point3D.py:35-39   cached by the Python shim: the reference
+ *                                                              re-constructs the matcher on every call)
+ *   matcher.knnMatch(des1, des2, k=2)                      slm_knn2_host (numpy/host memory in, host memory out)
+ *     tracking.py:22  keypoint.py:44  Point3D.py:40        slm_knn2 / slm_knn2_filter (device-resident fast path)
+ *   for m, n in matches: if m.distance < 0.7*n.distance    ratio_num/ratio_den arguments of slm_knn2_filter /
+ *     tracking.py:24-30  keypoint.py:45-51  Point3D.py:41-49   slm_knn2_host (integer form: den*d1 < num*d2)
+ *   [kp[m.queryIdx].pt for m in good] gathers              slm_compact_matches (device-side compaction of accepted rows)
+ *     tracking.py:32-33  keypoint.py:53-57  Point3D.py:50-52
+ *   (config 3: all keyframe pairs)                         slm_knn2_batched
+ *   (configs 4/5: train set sharded over GPUs)             slm_knn2_keys on each rank + slm_merge_top2 after the
+ *                                                          all-gather (tie order = (distance, global train index),
+ *                                                          OpenCV's (distance, imgIdx, trainIdx) collection order)
+ *
+ * Data layout
+ *   A descriptor is 32 bytes.  Device entry points take `const uint32_t*` pointing at uint32[n][8]
+ *   (a plain reinterpretation of the reference's uint8[n][32] rows, orb.py:23-24; little-endian,
+ *   popcount is byte-order agnostic).  Rows must be 16-byte aligned (any cudaMalloc'd or torch tensor is).
+ *   Results: idx int32[nq][2], dist int32[nq][2]; column 0 = nearest, column 1 = second nearest under
+ *   the order (distance, train index) ascending -- lowest train index wins ties, exactly as
+ *   cv2.BFMatcher(NORM_HAMMING).knnMatch.  A missing neighbour (nt < 2) is idx = -1, dist = -1, which
+ *   the Python shim turns into OpenCV's short rows.  accept uint8[nq] is the ratio / cross-check verdict.
+ *   Packed keys (sharded path): uint64 = (distance << 32) | global_train_index, SLM_KEY_NONE if missing.
+ *
+ * Conventions
+ *   Every function returns 0 (SLM_OK) or a negative slm_status; slm_last_error() returns a
+ *   thread-local message for the last failure.  `stream` is a cudaStream_t passed as void*
+ *   (NULL = legacy default stream).  Device entry points are asynchronous and stream-ordered;
+ *   *_host entry points synchronise before returning.  A ctx is not re-entrant: one ctx per
+ *   (host thread, device).  The library owns only its workspace (grown on demand); callers own all
+ *   input and output buffers; inputs are never written.  There is NO CPU fallback: without a
+ *   CUDA device every compute entry point fails with SLM_ERR_CUDA.
+ */
+#ifndef SLAMMATCH_H
+#define SLAMMATCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLM_VERSION 100           /* major*10000 + minor*100 + patch */
+#define SLM_DESC_WORDS 8          /* uint32 words per descriptor */
+#define SLM_DESC_BYTES 32
+#define SLM_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+typedef struct slm_ctx slm_ctx;
+
+typedef enum slm_status {
+    SLM_OK = 0,
+    SLM_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, ratio_den <= 0, ...) */
+    SLM_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...) */
+    SLM_ERR_NOMEM = -3,       /* workspace allocation failed */
+    SLM_ERR_UNSUPPORTED = -4  /* size beyond the supported range (global index must fit int32) */
+} slm_status;
+
+/* Distance-kernel variants (BASELINE.json north_star part (2)). */
+typedef enum slm_variant {
+    SLM_VARIANT_AUTO = 0,    /* pick per shape */
+    SLM_VARIANT_POPC = 1,    /* LOP3(XOR)+POPC on the integer pipe */
+    SLM_VARIANT_TENSOR = 2,  /* +-1 fp8 expansion + tcgen05.mma (TMEM accumulators) */
+    SLM_VARIANT_BMMA = 3     /* b1 AND.POPC mma.sync tiles (emulated by ptxas on sm_100a; kept for the A/B) */
+} slm_variant;
+
+/* Thread-local text of the last error returned on this thread ("" if none). */
+const char *slm_last_error(void);
+int slm_version(void);
+
+/* Replaces the matcher constructor (tracking.py:17).  `device` is a CUDA ordinal. */
+int slm_create(int device, slm_ctx **ctx_out);
+int slm_destroy(slm_ctx *ctx);
+/* Select the distance kernel for subsequent calls on this ctx (default SLM_VARIANT_AUTO). */
+int slm_set_variant(slm_ctx *ctx, int variant);
+/* The variant the last search on this ctx actually ran (resolves SLM_VARIANT_AUTO); 0 before any search. */
+int slm_last_variant(const slm_ctx *ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches evidence). */
+int64_t slm_launch_count(const slm_ctx *ctx);
+/*
+ * Optional timing of the dominant (distance) kernel: when enabled, every launch of it is bracketed by
+ * CUDA events on the launching stream.  slm_profile_read synchronises those events, returns the summed
+ * duration in milliseconds and the number of launches since the last read, and resets both.
+ */
+int slm_profile_enable(slm_ctx *ctx, int enable);
+int slm_profile_read(slm_ctx *ctx, double *kernel_ms_out, int64_t *launches_out);
+
+/*
+ * knnMatch(q, t, k=2), device-resident (tracking.py:22).  Global train index = train_index_base + row.
+ * nq, nt may be 0.  train_index_base + nt must be <= 2^31 - 1.
+ */
+int slm_knn2(slm_ctx *ctx, const uint32_t *q_dev, int64_t nq, const uint32_t *t_dev, int64_t nt,
+             int64_t train_index_base, int32_t *idx_out_dev, int32_t *dist_out_dev, void *stream);
+
+/* Same search, result as packed keys uint64[nq][2] (input of the cross-shard all-gather). */
+int slm_knn2_keys(slm_ctx *ctx, const uint32_t *q_dev, int64_t nq, const uint32_t *t_dev, int64_t nt,
+                  int64_t train_index_base, uint64_t *keys_out_dev, void *stream);
+
+/*
+ * knnMatch + the reference's ratio loop (tracking.py:24-30) + optional cross-check, one call.
+ *   accept[i] = has 2 neighbours && ratio_den*d1 < ratio_num*d2      (ratio_num <= 0 disables the ratio test:
+ *                                                                     then accept = has >= 1 neighbour)
+ *             && (cross_check == 0 || argmin_i' D[i', idx[i][0]] == i) (lowest query index on ties)
+ * (7,10) is the reference's 0.7; (3,4) is BASELINE config 1's 0.75.  idx/dist/accept may each be NULL.
+ */
+int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q_dev, int64_t nq, const uint32_t *t_dev, int64_t nt,
+                    int64_t train_index_base, int32_t ratio_num, int32_t ratio_den, int32_t cross_check,
+                    int32_t *idx_out_dev, int32_t *dist_out_dev, uint8_t *accept_out_dev, void *stream);
+
+/*
+ * Config 3 (local-mapping batch): desc_dev is uint32[n_frames][n_per_frame][8]; pairs_host is a HOST
+ * array int32[n_pairs][2] of (query frame, train frame).  Outputs are [n_pairs][n_per_frame][2] /
+ * [n_pairs][n_per_frame]; train indices are local to the train frame.
+ */
+int slm_knn2_batched(slm_ctx *ctx, const uint32_t *desc_dev, int64_t n_frames, int64_t n_per_frame,
+                     const int32_t *pairs_host, int64_t n_pairs, int32_t ratio_num, int32_t ratio_den,
+                     int32_t *idx_out_dev, int32_t *dist_out_dev, uint8_t *accept_out_dev, void *stream);
+
+/*
+ * Cross-shard merge after the all-gather: gathered_keys_dev is uint64[n_shards][nq][2]; the result is the
+ * top-2 in unsigned key order == (distance, global train index).  ratio as in slm_knn2_filter
+ * (accept_out_dev may be NULL).
+ */
+int slm_merge_top2(slm_ctx *ctx, const uint64_t *gathered_keys_dev, int32_t n_shards, int64_t nq,
+                   int32_t ratio_num, int32_t ratio_den, int32_t *idx_out_dev, int32_t *dist_out_dev,
+                   uint8_t *accept_out_dev, void *stream);
+
+/*
+ * Device-side compaction of accepted rows (the gathers at tracking.py:32-33 start from this list):
+ * writes (queryIdx, trainIdx, distance) int32 triples in ascending queryIdx order to matches_out_dev
+ * (capacity nq triples) and the count to count_out_dev (int32[1]).
+ * If stop_at_short_row != 0 the list is truncated at the first row with fewer than two neighbours,
+ * as the reference's swallowed ValueError does (tracking.py:25-30).
+ */
+int slm_compact_matches(slm_ctx *ctx, const int32_t *idx_dev, const int32_t *dist_dev,
+                        const uint8_t *accept_dev, int64_t nq, int32_t stop_at_short_row,
+                        int32_t *matches_out_dev, int32_t *count_out_dev, void *stream);
+
+/*
+ * Host-memory convenience: what the Python shim's knnMatch(des1, des2, k=2) calls.  q_host/t_host are
+ * uint8[n][32] in host memory (pinned or pageable; pageable memory is staged through the ctx's pinned
+ * buffers); outputs are host arrays.  Copies, kernels and the read-back run on the ctx's own stream and
+ * the call returns after they complete.  Any output pointer may be NULL.
+ */
+int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t *t_host, int64_t nt,
+                  int32_t ratio_num, int32_t ratio_den, int32_t cross_check,
+                  int32_t *idx_out_host, int32_t *dist_out_host, uint8_t *accept_out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMMATCH_H */

@@ -1,0 +1,359 @@
+// api.cu -- the extern "C" surface declared in include/slammatch.h.
+//
+// Host-side orchestration only: argument checks, workspace, variant dispatch, stream ordering.
+// There is no CPU implementation behind any entry point: without a CUDA device they fail.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "slm_internal.cuh"
+
+// ---- error plumbing ------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int slm_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int slm_buf_reserve(slm_ctx *ctx, slm_buf *buf, size_t bytes)
+{
+    (void)ctx;
+    if (bytes <= buf->bytes) return SLM_OK;
+    size_t want = bytes + bytes / 4 + 4096;  // slack so that slowly growing inputs do not realloc each call
+    if (buf->p) {
+        SLM_CUDA(cudaDeviceSynchronize());
+        SLM_CUDA(cudaFree(buf->p));
+        buf->p = nullptr;
+        buf->bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&buf->p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        buf->p = nullptr;
+        return slm_fail(SLM_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    buf->bytes = want;
+    return SLM_OK;
+}
+
+static int pin_reserve(slm_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->pin_bytes) return SLM_OK;
+    if (ctx->pin) {
+        SLM_CUDA(cudaDeviceSynchronize());
+        SLM_CUDA(cudaFreeHost(ctx->pin));
+        ctx->pin = nullptr;
+        ctx->pin_bytes = 0;
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&ctx->pin, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        ctx->pin = nullptr;
+        return slm_fail(SLM_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    ctx->pin_bytes = want;
+    return SLM_OK;
+}
+
+int slm_prof_begin(slm_ctx *ctx, cudaStream_t stream)
+{
+    if (!ctx->profile || ctx->prof_n >= slm_ctx::kMaxProf) return SLM_OK;
+    if (!ctx->prof_ev) {
+        ctx->prof_ev = new (std::nothrow) cudaEvent_t[2 * slm_ctx::kMaxProf];
+        if (!ctx->prof_ev) return slm_fail(SLM_ERR_NOMEM, "out of host memory");
+        for (int i = 0; i < 2 * slm_ctx::kMaxProf; ++i) SLM_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+    }
+    SLM_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], stream));
+    return SLM_OK;
+}
+
+int slm_prof_end(slm_ctx *ctx, cudaStream_t stream)
+{
+    if (!ctx->profile || ctx->prof_n >= slm_ctx::kMaxProf || !ctx->prof_ev) return SLM_OK;
+    SLM_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], stream));
+    ctx->prof_n += 1;
+    return SLM_OK;
+}
+
+static int check_ctx(slm_ctx *ctx)
+{
+    if (!ctx) return slm_fail(SLM_ERR_INVALID, "ctx is NULL");
+    SLM_CUDA(cudaSetDevice(ctx->device));
+    return SLM_OK;
+}
+
+static int check_sizes(int64_t nq, int64_t nt, int64_t base)
+{
+    if (nq < 0 || nt < 0 || base < 0) return slm_fail(SLM_ERR_INVALID, "negative size (nq=%lld nt=%lld base=%lld)",
+                                                       (long long)nq, (long long)nt, (long long)base);
+    if (nq > 0x7FFFFFFFll || base + nt > 0x7FFFFFFFll)
+        return slm_fail(SLM_ERR_UNSUPPORTED, "indices must fit int32 (nq=%lld base+nt=%lld)", (long long)nq,
+                        (long long)(base + nt));
+    return SLM_OK;
+}
+
+__global__ void fill_keys_none_kernel(unsigned long long *keys, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = kKeyNone;
+}
+
+// Variant dispatch: produce packed keys uint64[nq][2] for one problem.
+static int knn2_keys_dispatch(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
+                              int64_t base, uint64_t *keys_out, cudaStream_t stream)
+{
+    if (nq == 0) return SLM_OK;
+    if (nt == 0) {
+        fill_keys_none_kernel<<<(unsigned)((2 * nq + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<unsigned long long *>(keys_out), 2 * nq);
+        SLM_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        return SLM_OK;
+    }
+    if (((uintptr_t)q & 15) || ((uintptr_t)t & 15))
+        return slm_fail(SLM_ERR_INVALID, "descriptor pointers must be 16-byte aligned");
+    switch (ctx->variant) {
+    case SLM_VARIANT_TENSOR:
+        return slm_tc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
+    case SLM_VARIANT_BMMA:
+        return slm_bmma_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
+    case SLM_VARIANT_POPC:
+        return slm_popc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
+    default:
+        return slm_auto_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
+    }
+}
+
+// ---- public ABI ----------------------------------------------------------------------------------
+extern "C" {
+
+const char *slm_last_error(void) { return g_err; }
+int slm_version(void) { return SLM_VERSION; }
+
+int slm_create(int device, slm_ctx **ctx_out)
+{
+    if (!ctx_out) return slm_fail(SLM_ERR_INVALID, "ctx_out is NULL");
+    *ctx_out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return slm_fail(SLM_ERR_CUDA, "no CUDA device available (%s); libslammatch has no CPU path",
+                        e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return slm_fail(SLM_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    SLM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SLM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return slm_fail(SLM_ERR_CUDA, "device %d is sm_%d%d; libslammatch is built for sm_100a (B200) only", device,
+                        prop.major, prop.minor);
+    slm_ctx *ctx = new (std::nothrow) slm_ctx();
+    if (!ctx) return slm_fail(SLM_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    SLM_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming));
+    SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming));
+    *ctx_out = ctx;
+    return SLM_OK;
+}
+
+int slm_destroy(slm_ctx *ctx)
+{
+    if (!ctx) return SLM_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    slm_buf *bufs[] = {&ctx->scratch, &ctx->keys, &ctx->rev, &ctx->misc, &ctx->io};
+    for (slm_buf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->prof_ev) {
+        for (int i = 0; i < 2 * slm_ctx::kMaxProf; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+        delete[] ctx->prof_ev;
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    for (cudaEvent_t ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    delete ctx;
+    (void)cudaGetLastError();
+    return SLM_OK;
+}
+
+int slm_set_variant(slm_ctx *ctx, int variant)
+{
+    if (!ctx) return slm_fail(SLM_ERR_INVALID, "ctx is NULL");
+    if (variant < SLM_VARIANT_AUTO || variant > SLM_VARIANT_BMMA)
+        return slm_fail(SLM_ERR_INVALID, "unknown variant %d", variant);
+    ctx->variant = variant;
+    return SLM_OK;
+}
+
+int64_t slm_launch_count(const slm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int slm_last_variant(const slm_ctx *ctx) { return ctx ? ctx->last_variant : 0; }
+
+int slm_profile_enable(slm_ctx *ctx, int enable)
+{
+    if (!ctx) return slm_fail(SLM_ERR_INVALID, "ctx is NULL");
+    ctx->profile = enable ? 1 : 0;
+    return SLM_OK;
+}
+
+int slm_profile_read(slm_ctx *ctx, double *kernel_ms_out, int64_t *launches_out)
+{
+    SLM_TRY(check_ctx(ctx));
+    double total = 0.0;
+    for (int i = 0; i < ctx->prof_n; ++i) {
+        float ms = 0.f;
+        SLM_CUDA(cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+        SLM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        total += ms;
+    }
+    if (kernel_ms_out) *kernel_ms_out = total;
+    if (launches_out) *launches_out = ctx->prof_n;
+    ctx->prof_n = 0;
+    return SLM_OK;
+}
+
+int slm_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                  uint64_t *keys_out, void *stream)
+{
+    SLM_TRY(check_ctx(ctx));
+    SLM_TRY(check_sizes(nq, nt, base));
+    if (nq == 0) return SLM_OK;
+    if (!q || !keys_out || (nt > 0 && !t)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    return knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys_out, (cudaStream_t)stream);
+}
+
+int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                    int32_t ratio_num, int32_t ratio_den, int32_t cross_check, int32_t *idx_out,
+                    int32_t *dist_out, uint8_t *accept_out, void *stream_)
+{
+    SLM_TRY(check_ctx(ctx));
+    SLM_TRY(check_sizes(nq, nt, base));
+    if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
+    if (nq == 0) return SLM_OK;
+    if (!q || (nt > 0 && !t)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)nq * 16));
+    uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
+    SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys, stream));
+    const uint64_t *rev = nullptr;
+    if (cross_check && accept_out && nt > 0) {
+        // reverse search: every train row against all queries (lowest query index wins ties)
+        SLM_TRY(slm_buf_reserve(ctx, &ctx->rev, (size_t)nt * 16));
+        SLM_TRY(knn2_keys_dispatch(ctx, t, nt, q, nq, 0, reinterpret_cast<uint64_t *>(ctx->rev.p), stream));
+        rev = reinterpret_cast<const uint64_t *>(ctx->rev.p);
+    }
+    return slm_finalize(ctx, keys, nq, ratio_num, ratio_den, rev, nt, base, idx_out, dist_out, accept_out, stream);
+}
+
+int slm_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+             int32_t *idx_out, int32_t *dist_out, void *stream)
+{
+    return slm_knn2_filter(ctx, q, nq, t, nt, base, 0, 1, 0, idx_out, dist_out, nullptr, stream);
+}
+
+int slm_knn2_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_frames, int64_t n_per_frame,
+                     const int32_t *pairs_host, int64_t n_pairs, int32_t ratio_num, int32_t ratio_den,
+                     int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, void *stream_)
+{
+    SLM_TRY(check_ctx(ctx));
+    if (n_frames < 0 || n_per_frame < 0 || n_pairs < 0) return slm_fail(SLM_ERR_INVALID, "negative size");
+    if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
+    if (n_pairs == 0 || n_per_frame == 0) return SLM_OK;
+    if (!desc || !pairs_host) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    if (n_per_frame > 0x7FFFFFFFll || n_pairs * n_per_frame > 0x7FFFFFFFll)
+        return slm_fail(SLM_ERR_UNSUPPORTED, "batch too large");
+    for (int64_t i = 0; i < 2 * n_pairs; ++i)
+        if (pairs_host[i] < 0 || pairs_host[i] >= n_frames)
+            return slm_fail(SLM_ERR_INVALID, "pair %lld references frame %d outside [0,%lld)", (long long)(i / 2),
+                            pairs_host[i], (long long)n_frames);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t rows = n_pairs * n_per_frame;
+    SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)rows * 16));
+    SLM_TRY(slm_buf_reserve(ctx, &ctx->misc, (size_t)n_pairs * 8));
+    SLM_TRY(pin_reserve(ctx, (size_t)n_pairs * 8));
+    // the pinned copy must not be overwritten while a previous call's H2D is in flight
+    SLM_CUDA(cudaEventSynchronize(ctx->ev[0]));
+    memcpy(ctx->pin, pairs_host, (size_t)n_pairs * 8);
+    SLM_CUDA(cudaMemcpyAsync(ctx->misc.p, ctx->pin, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, stream));
+    SLM_CUDA(cudaEventRecord(ctx->ev[0], stream));
+    uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
+    SLM_TRY(slm_batched_knn2_keys(ctx, desc, n_per_frame, reinterpret_cast<const int32_t *>(ctx->misc.p), n_pairs,
+                                  keys, stream));
+    return slm_finalize(ctx, keys, rows, ratio_num, ratio_den, nullptr, 0, 0, idx_out, dist_out, accept_out, stream);
+}
+
+int slm_merge_top2(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int64_t nq, int32_t ratio_num,
+                   int32_t ratio_den, int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, void *stream_)
+{
+    SLM_TRY(check_ctx(ctx));
+    if (n_shards <= 0 || nq < 0) return slm_fail(SLM_ERR_INVALID, "n_shards must be > 0 and nq >= 0");
+    if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
+    if (nq == 0) return SLM_OK;
+    if (!gathered) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)nq * 16));
+    uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
+    SLM_TRY(slm_merge_keys(ctx, gathered, n_shards, nq, keys, stream));
+    return slm_finalize(ctx, keys, nq, ratio_num, ratio_den, nullptr, 0, 0, idx_out, dist_out, accept_out, stream);
+}
+
+int slm_compact_matches(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
+                        int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, void *stream)
+{
+    SLM_TRY(check_ctx(ctx));
+    if (nq < 0) return slm_fail(SLM_ERR_INVALID, "negative size");
+    if (!count_out || (nq > 0 && (!idx || !dist || !accept || !matches_out)))
+        return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    return slm_compact(ctx, idx, dist, accept, nq, stop_at_short_row, matches_out, count_out, (cudaStream_t)stream);
+}
+
+int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t *t_host, int64_t nt,
+                  int32_t ratio_num, int32_t ratio_den, int32_t cross_check, int32_t *idx_out,
+                  int32_t *dist_out, uint8_t *accept_out)
+{
+    SLM_TRY(check_ctx(ctx));
+    SLM_TRY(check_sizes(nq, nt, 0));
+    if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
+    if (nq == 0) return SLM_OK;
+    if (!q_host || (nt > 0 && !t_host)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    cudaStream_t s = ctx->own_stream;
+    // device layout: [q | t | idx | dist | accept], every block 256-byte aligned
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t q_b = up((size_t)nq * 32), t_b = up((size_t)nt * 32), i_b = up((size_t)nq * 8), a_b = up((size_t)nq);
+    SLM_TRY(slm_buf_reserve(ctx, &ctx->io, q_b + t_b + 2 * i_b + a_b));
+    uint8_t *base = reinterpret_cast<uint8_t *>(ctx->io.p);
+    uint32_t *q_dev = reinterpret_cast<uint32_t *>(base);
+    uint32_t *t_dev = reinterpret_cast<uint32_t *>(base + q_b);
+    int32_t *idx_dev = reinterpret_cast<int32_t *>(base + q_b + t_b);
+    int32_t *dist_dev = reinterpret_cast<int32_t *>(base + q_b + t_b + i_b);
+    uint8_t *acc_dev = base + q_b + t_b + 2 * i_b;
+    // results come back through pinned staging so the D2H copies are truly asynchronous
+    SLM_TRY(pin_reserve(ctx, 2 * i_b + a_b));
+    uint8_t *pin = reinterpret_cast<uint8_t *>(ctx->pin);
+    SLM_CUDA(cudaEventSynchronize(ctx->ev[0]));  // a batched call may still be reading the pinned block
+
+    SLM_CUDA(cudaMemcpyAsync(q_dev, q_host, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (nt > 0) SLM_CUDA(cudaMemcpyAsync(t_dev, t_host, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    SLM_TRY(slm_knn2_filter(ctx, q_dev, nq, t_dev, nt, 0, ratio_num, ratio_den, cross_check, idx_dev, dist_dev,
+                            accept_out ? acc_dev : nullptr, s));
+    if (idx_out) SLM_CUDA(cudaMemcpyAsync(pin, idx_dev, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    if (dist_out) SLM_CUDA(cudaMemcpyAsync(pin + i_b, dist_dev, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+    if (accept_out) SLM_CUDA(cudaMemcpyAsync(pin + 2 * i_b, acc_dev, (size_t)nq, cudaMemcpyDeviceToHost, s));
+    SLM_CUDA(cudaStreamSynchronize(s));
+    if (idx_out) memcpy(idx_out, pin, (size_t)nq * 8);
+    if (dist_out) memcpy(dist_out, pin + i_b, (size_t)nq * 8);
+    if (accept_out) memcpy(accept_out, pin + 2 * i_b, (size_t)nq);
+    return SLM_OK;
+}
+
+}  // extern "C"

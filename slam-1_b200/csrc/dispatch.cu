@@ -1,0 +1,31 @@
+// dispatch.cu -- shape policy for SLM_VARIANT_AUTO and the batched (config 3) entry point.
+#include "slm_internal.cuh"
+
+int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
+                       int64_t base, uint64_t *keys_out, cudaStream_t stream)
+{
+    return slm_popc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
+}
+
+int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
+                          int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream)
+{
+    // grid.y / grid.z carry the pair index: chunk long pair lists
+    const int64_t kMaxPairs = 32768;
+    for (int64_t p0 = 0; p0 < n_pairs; p0 += kMaxPairs) {
+        int64_t n = n_pairs - p0 < kMaxPairs ? n_pairs - p0 : kMaxPairs;
+        if (ctx->variant == SLM_VARIANT_TENSOR)
+            SLM_TRY(slm_tc_knn2_keys_batched(ctx, desc, n_per_frame, pairs_dev + 2 * p0, n,
+                                             keys_out + 2 * p0 * n_per_frame, stream));
+        else
+            SLM_TRY(slm_popc_knn2_keys_batched(ctx, desc, n_per_frame, pairs_dev + 2 * p0, n,
+                                               keys_out + 2 * p0 * n_per_frame, stream));
+    }
+    return SLM_OK;
+}
+
+// Placeholders until the variants land (they fail loudly; nothing falls back silently).
+int slm_bmma_knn2_keys(slm_ctx *, const uint32_t *, int64_t, const uint32_t *, int64_t, int64_t, uint64_t *, cudaStream_t)
+{
+    return slm_fail(SLM_ERR_UNSUPPORTED, "SLM_VARIANT_BMMA is not built in this library");
+}

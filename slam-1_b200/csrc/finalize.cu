@@ -1,0 +1,140 @@
+// finalize.cu -- everything after the distance kernels, shared by all variants:
+//   * packed keys -> (idx, dist) + the reference's Lowe ratio test in integer form
+//     (`if m.distance < 0.7 * n.distance`, tracking.py:27 / keypoint.py:48 / Point3D.py:44;
+//     den*d1 < num*d2 is exact for every d in 0..256) + cross-check;
+//   * cross-shard merge of all-gathered keys (order = (distance, global train index));
+//   * ordered compaction of accepted rows (the `good` list of tracking.py:24-30).
+#include "slm_internal.cuh"
+
+namespace {
+
+__global__ void finalize_kernel(const unsigned long long *keys, long long n, int ratio_num, int ratio_den,
+                                const unsigned long long *rev_keys, long long nt, long long base,
+                                int *idx_out, int *dist_out, unsigned char *accept_out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ulonglong2 k = reinterpret_cast<const ulonglong2 *>(keys)[i];
+    const bool has1 = k.x != kKeyNone, has2 = k.y != kKeyNone;
+    int i1 = has1 ? (int)(k.x & 0xFFFFFFFFull) : -1, d1 = has1 ? (int)(k.x >> 32) : -1;
+    int i2 = has2 ? (int)(k.y & 0xFFFFFFFFull) : -1, d2 = has2 ? (int)(k.y >> 32) : -1;
+    if (idx_out) reinterpret_cast<int2 *>(idx_out)[i] = make_int2(i1, i2);
+    if (dist_out) reinterpret_cast<int2 *>(dist_out)[i] = make_int2(d1, d2);
+    if (accept_out) {
+        bool ok = ratio_num > 0 ? (has1 && has2 && (long long)ratio_den * d1 < (long long)ratio_num * d2) : has1;
+        if (ok && rev_keys != nullptr) {
+            long long j = (long long)i1 - base;
+            ok = j >= 0 && j < nt && (long long)(rev_keys[2 * j] & 0xFFFFFFFFull) == i;
+        }
+        accept_out[i] = ok ? 1 : 0;
+    }
+}
+
+__global__ void merge_keys_kernel(const unsigned long long *gathered, int n_shards, long long nq,
+                                  unsigned long long *keys_out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    unsigned long long k1 = kKeyNone, k2 = kKeyNone;
+    for (int s = 0; s < n_shards; ++s) {
+        ulonglong2 v = reinterpret_cast<const ulonglong2 *>(gathered)[(long long)s * nq + i];
+        unsigned long long m = max(k1, v.x);
+        k1 = min(k1, v.x);
+        k2 = min(k2, m);
+        m = max(k1, v.y);
+        k1 = min(k1, v.y);
+        k2 = min(k2, m);
+    }
+    reinterpret_cast<ulonglong2 *>(keys_out)[i] = make_ulonglong2(k1, k2);
+}
+
+// Ordered compaction by one CTA: block-wide exclusive scan over 1024-row chunks.
+constexpr int kCompactThreads = 1024;
+__global__ void __launch_bounds__(kCompactThreads)
+compact_kernel(const int *idx, const int *dist, const unsigned char *accept, long long nq, int stop_at_short_row,
+               int *matches_out, int *count_out)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int chunk_base;
+    __shared__ long long first_short;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { chunk_base = 0; first_short = nq; }
+    __syncthreads();
+    if (stop_at_short_row) {
+        long long mine = nq;
+        for (long long i = tid; i < nq; i += kCompactThreads)
+            if (idx[2 * i] < 0 || idx[2 * i + 1] < 0) { mine = i; break; }
+        if (mine < nq) atomicMin(&first_short, mine);
+        __syncthreads();
+    }
+    const long long limit = first_short;
+    for (long long c0 = 0; c0 < limit; c0 += kCompactThreads) {
+        long long i = c0 + tid;
+        int flag = (i < limit && accept[i]) ? 1 : 0;
+        int incl = flag;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= o) wi += v;
+            }
+            warp_sums[lane] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        int pos = chunk_base + warp_sums[warp] + incl - flag;
+        if (flag) {
+            matches_out[3 * pos + 0] = (int)i;
+            matches_out[3 * pos + 1] = idx[2 * i];
+            matches_out[3 * pos + 2] = dist[2 * i];
+        }
+        __syncthreads();
+        if (tid == kCompactThreads - 1) chunk_base = pos + flag;
+        __syncthreads();
+    }
+    if (tid == 0) *count_out = chunk_base;
+}
+
+}  // namespace
+
+int slm_finalize(slm_ctx *ctx, const uint64_t *keys, int64_t n, int32_t ratio_num, int32_t ratio_den,
+                 const uint64_t *rev_keys, int64_t nt, int64_t train_index_base, int32_t *idx_out,
+                 int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream)
+{
+    if (n <= 0) return SLM_OK;
+    finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const unsigned long long *>(keys), n, ratio_num, ratio_den,
+        reinterpret_cast<const unsigned long long *>(rev_keys), nt, train_index_base, idx_out, dist_out, accept_out);
+    SLM_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SLM_OK;
+}
+
+int slm_merge_keys(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int64_t nq, uint64_t *keys_out,
+                   cudaStream_t stream)
+{
+    if (nq <= 0) return SLM_OK;
+    merge_keys_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const unsigned long long *>(gathered), n_shards, nq,
+        reinterpret_cast<unsigned long long *>(keys_out));
+    SLM_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SLM_OK;
+}
+
+int slm_compact(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
+                int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, cudaStream_t stream)
+{
+    compact_kernel<<<1, kCompactThreads, 0, stream>>>(idx, dist, accept, nq, stop_at_short_row, matches_out, count_out);
+    SLM_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SLM_OK;
+}

@@ -1,0 +1,372 @@
+// knn2_tc.cu -- variant T: exact Hamming 2-NN on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Replaces the O(nq*nt) distance evaluation inside matcher.knnMatch(des1, des2, k=2)
+// (reference call sites tracking.py:22, keypoint.py:44, Point3D.py:40; exhaustive semantics).
+//
+// Idea.  The all-pairs Hamming distance is a dense binary contraction.  Expanding every descriptor bit
+// to fp8 +1.0 / -1.0 gives   dot(x_i, y_j) = 256 - 2 * Hamming(q_i, t_j)   exactly (small integers in an
+// fp32 accumulator), so a 128 (queries) x 256 (train) x 256 (bits) "job" is 8 tcgen05.mma instructions.
+// sm_100a has no native 1-bit tensor op (ptxas emulates mma.sync b1 with IMMA + bit twiddling,
+// SURVEY.md H1); the expansion is instead done ONCE per operand tile, in shared memory.
+//
+// One CTA = one work item = (query group of up to 3 x 128 rows) x (contiguous train range), 1 CTA / SM:
+//   warps 0-7   epilogue: TMEM -> registers (tcgen05.ld 32x32b.x32), branch-free candidate tracking
+//   warps 8-15  expanders: packed bits (LDG.128, coalesced 32-B rows) -> +-1 fp8 rows in the K-major
+//               no-swizzle UMMA layout (conflict-free STS.128), double-buffered train stages
+//   warp  16    one elected thread issues tcgen05.mma (M=128, N=256, K=32) into two 256-column TMEM
+//               accumulators and tcgen05.commit's onto mbarriers
+// Pipelines (all mbarrier): a_full, b_full[2]/b_empty[2] (expanders <-> MMA), acc_full[2]/acc_empty[2]
+// (MMA <-> epilogue).  HBM traffic is the packed descriptors only; the 8x expanded operands never
+// leave the SM.
+//
+// Epilogue.  Thread = one query row (one TMEM lane); it sees its row's dot products 32 columns at a time.
+// Tracking (distance, index) per element would cost more ALU than the MMA leaves room for, so the kernel
+// keeps, per row, only the best two 32-column CHUNKS by (max dot desc, chunk index asc), packed into one
+// fp32 (dot * 8192 + 8191 - chunk; exact, < 2^24) and updated with three FMNMX.  The exact top-2 rows
+// (distance asc, index asc) of a range always lie inside its best two chunks, so a tiny second kernel
+// re-scores just those candidate rows with XOR+POPC and applies the reference tie-break bit-exactly.
+// Cost per element: ~0.5 FMNMX3; data-independent (no divergence on adversarial inputs).
+#include <cfloat>
+#include "slm_internal.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kTileN = 256;
+constexpr int kChunk = 32;
+constexpr int kChunksPerTile = kTileN / kChunk;   // 8
+constexpr int kMaxMT = 3;                          // query tiles resident per CTA
+constexpr int kEpiWarps = 8;
+constexpr int kExpWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;        // 256
+constexpr int kExpThreads = kExpWarps * 32;        // 256
+constexpr int kThreads = kEpiThreads + kExpThreads + 32;   // 544
+constexpr uint32_t kATileBytes = kTileM * 256;     // 32 KB
+constexpr uint32_t kBTileBytes = kTileN * 256;     // 64 KB
+constexpr int kMaxRangeTiles = 1024;               // 8192 chunks -> 13 bits of the packed fp32 key
+constexpr float kKeyScale = 8192.0f;
+
+struct TcParams {
+    const uint32_t *q, *t;        // single problem
+    const uint32_t *desc;         // batched: uint32[n_frames][n_per_frame][8] (else nullptr)
+    const int32_t *pairs;         // batched: device int32[n_prob][2]
+    long long frame_words;
+    int nq, nt;
+    int n_prob;
+    int mt;                       // query tiles per group (1..kMaxMT)
+    int n_groups;                 // ceil(nq / (128 * mt))
+    int range_tiles, n_ranges;
+    float2 *cand;                 // [n_prob][n_ranges][2][nq]: best two chunk keys per epilogue set
+};
+
+struct TcBarriers {
+    uint64_t a_full;
+    uint64_t b_full[2], b_empty[2];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float max32(const uint32_t (&v)[32])
+{
+    float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+#pragma unroll
+    for (int j = 4; j < 32; j += 8) {   // 4 independent chains of 3-input max (FMNMX3)
+        m0 = fmaxf(fmaxf(m0, __uint_as_float(v[j + 0])), __uint_as_float(v[j + 1]));
+        m1 = fmaxf(fmaxf(m1, __uint_as_float(v[j + 2])), __uint_as_float(v[j + 3]));
+        m2 = fmaxf(fmaxf(m2, __uint_as_float(v[j + 4])), __uint_as_float(v[j + 5]));
+        m3 = fmaxf(fmaxf(m3, __uint_as_float(v[j + 6])), __uint_as_float(v[j + 7]));
+    }
+    m0 = fmaxf(fmaxf(m0, __uint_as_float(v[28])), __uint_as_float(v[29]));
+    m1 = fmaxf(fmaxf(m1, __uint_as_float(v[30])), __uint_as_float(v[31]));
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sA = smem;                                   // MT tiles of 32 KB
+    uint8_t *sB = smem + MT * kATileBytes;                // 2 stages of 64 KB
+    TcBarriers *bars = reinterpret_cast<TcBarriers *>(smem + MT * kATileBytes + 2 * kBTileBytes);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int range = blockIdx.x / p.n_groups;
+    const int group = blockIdx.x % p.n_groups;
+
+    const uint32_t *q = p.q;
+    const uint32_t *t = p.t;
+    if (p.desc != nullptr) {
+        int2 pr = reinterpret_cast<const int2 *>(p.pairs)[blockIdx.y];
+        q = p.desc + (long long)pr.x * p.frame_words;
+        t = p.desc + (long long)pr.y * p.frame_words;
+    }
+
+    const int q_first = group * (MT * kTileM);
+    const int mt_here = min(MT, (p.nq - q_first + kTileM - 1) / kTileM);     // >= 1
+    const int col_first = range * p.range_tiles * kTileN;
+    const int col_end = min(p.nt, col_first + p.range_tiles * kTileN);
+    const int n_tiles = (col_end - col_first + kTileN - 1) / kTileN;         // >= 1
+
+    if (tid == 0) {
+        tc::mbar_init(&bars->a_full, kExpThreads);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&bars->b_full[s], kExpThreads);
+            tc::mbar_init(&bars->b_empty[s], 1);
+            tc::mbar_init(&bars->acc_full[s], 1);
+            tc::mbar_init(&bars->acc_empty[s], kEpiThreads);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == kEpiWarps + kExpWarps) tc::tmem_alloc(&bars->tmem_base, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp < kEpiWarps) {
+        // ===================== epilogue: candidate chunks per query row =====================
+        const int set = warp >> 2, quad = warp & 3;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        float b1[MT], b2[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { b1[m] = -FLT_MAX; b2[m] = -FLT_MAX; }
+        int job = 0;
+        for (int bt = 0; bt < n_tiles; ++bt) {
+            const int valid_cols = min(kTileN, col_end - (col_first + bt * kTileN));
+            const int n_chunks = (valid_cols + kChunk - 1) / kChunk;
+            const float chunk_bias = (float)(8191 - bt * kChunksPerTile);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                if (m < mt_here) {
+                    const int ab = job & 1;
+                    tc::mbar_wait(&bars->acc_full[ab], (job >> 1) & 1, 10 + ab);
+                    tc::tc_fence_after();
+#pragma unroll
+                    for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
+                        const int c = 2 * cc + set;
+                        if (c < n_chunks) {
+                            uint32_t v[32];
+                            tc::tmem_ld32(lane_addr + ab * kTileN + c * kChunk, v);
+                            const float key = fmaf(max32(v), kKeyScale, chunk_bias - (float)c);
+                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                            b1[m] = fmaxf(b1[m], key);
+                        }
+                    }
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(&bars->acc_empty[ab]);
+                    ++job;
+                }
+            }
+        }
+        float2 *cand = p.cand + (((long long)blockIdx.y * p.n_ranges + range) * 2 + set) * (long long)p.nq;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const int qi = q_first + m * kTileM + quad * 32 + lane;
+            if (m < mt_here && qi < p.nq) cand[qi] = make_float2(b1[m], b2[m]);
+        }
+    } else if (warp < kEpiWarps + kExpWarps) {
+        // ===================== expanders: packed bits -> +-1 fp8 operand tiles =====================
+        const int et = tid - kEpiThreads;   // 0..255
+        const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
+        for (int r = et; r < mt_here * kTileM; r += kExpThreads) {
+            const int qi = min(q_first + r, p.nq - 1);
+            const uint4 *src = reinterpret_cast<const uint4 *>(q + (long long)qi * 8);
+            uint4 d0 = __ldg(src), d1 = __ldg(src + 1);
+            tc::expand_row_to_smem(sA_addr + (uint32_t)(r / kTileM) * kATileBytes, r % kTileM, d0, d1);
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive(&bars->a_full);
+
+        auto load_row = [&](int bt, uint4 &d0, uint4 &d1) {
+            const int row = min(col_first + bt * kTileN + et, p.nt - 1);
+            const uint4 *src = reinterpret_cast<const uint4 *>(t + (long long)row * 8);
+            d0 = __ldg(src);
+            d1 = __ldg(src + 1);
+        };
+        uint4 n0, n1;
+        load_row(0, n0, n1);
+        for (int bt = 0; bt < n_tiles; ++bt) {
+            const int s = bt & 1;
+            const uint4 c0 = n0, c1 = n1;
+            if (bt + 1 < n_tiles) load_row(bt + 1, n0, n1);      // prefetch the next tile's row
+            tc::mbar_wait(&bars->b_empty[s], ((bt >> 1) & 1) ^ 1, 20 + s);
+            tc::expand_row_to_smem(sB_addr + (uint32_t)s * kBTileBytes, et, c0, c1);
+            tc::fence_proxy_async();
+            tc::mbar_arrive(&bars->b_full[s]);
+        }
+    } else {
+        // ===================== MMA issuer: one elected thread =====================
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_e4m3_f32(kTileM, kTileN);
+            const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
+            tc::mbar_wait(&bars->a_full, 0, 30);
+            tc::tc_fence_after();
+            int job = 0;
+            for (int bt = 0; bt < n_tiles; ++bt) {
+                const int s = bt & 1;
+                tc::mbar_wait(&bars->b_full[s], (bt >> 1) & 1, 31 + s);
+                tc::tc_fence_after();
+                for (int m = 0; m < mt_here; ++m) {
+                    const int ab = job & 1;
+                    tc::mbar_wait(&bars->acc_empty[ab], ((job >> 1) & 1) ^ 1, 33 + ab);
+                    tc::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t ad = tc::smem_desc(sA_addr + (uint32_t)m * kATileBytes + k * 2 * tc::kLBO);
+                        const uint64_t bd = tc::smem_desc(sB_addr + (uint32_t)s * kBTileBytes + k * 2 * tc::kLBO);
+                        tc::umma_f8(tmem + ab * kTileN, ad, bd, idesc, k > 0 ? 1u : 0u);
+                    }
+                    tc::umma_commit(&bars->acc_full[ab]);
+                    ++job;
+                }
+                tc::umma_commit(&bars->b_empty[s]);
+            }
+        }
+        __syncwarp();
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == kEpiWarps + kExpWarps) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---- refine: exact re-scoring of the candidate chunks -------------------------------------------------
+__device__ __forceinline__ void top2_insert(unsigned long long &k1, unsigned long long &k2, unsigned long long key)
+{
+    unsigned long long m = max(k1, key);
+    k1 = min(k1, key);
+    k2 = min(k2, m);
+}
+
+// One warp per (problem, query).  Candidate chunk keys are decoded, the 32 rows of every candidate chunk
+// are re-scored with XOR+POPC (one row per lane) and reduced to the exact top-2 by (distance, index).
+__global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long base, unsigned long long *keys_out)
+{
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+    if (gw >= (long long)p.n_prob * p.nq) return;
+    const int prob = (int)(gw / p.nq);
+    const int qi = (int)(gw % p.nq);
+    const uint32_t *q = p.q;
+    const uint32_t *t = p.t;
+    if (p.desc != nullptr) {
+        int2 pr = reinterpret_cast<const int2 *>(p.pairs)[prob];
+        q = p.desc + (long long)pr.x * p.frame_words;
+        t = p.desc + (long long)pr.y * p.frame_words;
+    }
+    const uint4 *qs = reinterpret_cast<const uint4 *>(q + (long long)qi * 8);
+    const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
+
+    unsigned long long k1 = kKeyNone, k2 = kKeyNone;
+    const int n_cand = p.n_ranges * 4;   // (range, set, slot)
+    const float *cand = reinterpret_cast<const float *>(p.cand) + (long long)prob * p.n_ranges * 4 * (long long)p.nq;
+    for (int c0 = 0; c0 < n_cand; c0 += 32) {
+        // each lane fetches one candidate key, then the warp walks them together
+        int my_col = -1;
+        const int ci = c0 + lane;
+        if (ci < n_cand) {
+            const int r = ci >> 2, set = (ci >> 1) & 1, slot = ci & 1;
+            const float key = cand[(((long long)r * 2 + set) * p.nq + qi) * 2 + slot];
+            if (key > -1.0e30f) {
+                const int ki = (int)key + 256 * 8192;
+                const int chunk = 8191 - (ki & 8191);
+                my_col = (r * p.range_tiles * kTileN) + chunk * kChunk;
+            }
+        }
+        const int n_here = min(32, n_cand - c0);
+        for (int j = 0; j < n_here; ++j) {
+            const int col = __shfl_sync(0xFFFFFFFFu, my_col, j);
+            if (col < 0) continue;
+            const int row = col + lane;
+            if (row < p.nt) {
+                const uint4 *ts = reinterpret_cast<const uint4 *>(t + (long long)row * 8);
+                const uint4 ta = __ldg(ts), tb = __ldg(ts + 1);
+                const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                                   __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+                top2_insert(k1, k2, ((unsigned long long)d << 32) | (unsigned long long)(base + row));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o);
+        const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
+        top2_insert(k1, k2, o1);
+        top2_insert(k1, k2, o2);
+    }
+    if (lane == 0) reinterpret_cast<ulonglong2 *>(keys_out)[gw] = make_ulonglong2(k1, k2);
+}
+
+template <int MT>
+int launch_tc(const TcParams &p, int n_prob, cudaStream_t stream)
+{
+    const size_t smem = (size_t)MT * kATileBytes + 2 * kBTileBytes + sizeof(TcBarriers) + 64;
+    SLM_CUDA(cudaFuncSetAttribute(knn2_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(p.n_groups * p.n_ranges), (unsigned)n_prob);
+    knn2_tc_kernel<MT><<<grid, kThreads, smem, stream>>>(p);
+    SLM_CUDA(cudaGetLastError());
+    return SLM_OK;
+}
+
+int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_out, cudaStream_t stream)
+{
+    ctx->last_variant = SLM_VARIANT_TENSOR;
+    p.n_prob = n_prob;
+    const int m_tiles = (p.nq + kTileM - 1) / kTileM;
+    p.mt = m_tiles >= kMaxMT ? kMaxMT : m_tiles;
+    p.n_groups = (m_tiles + p.mt - 1) / p.mt;
+    const int n_tiles = (p.nt + kTileN - 1) / kTileN;
+    // ~4 work items per SM when there is enough work; ranges of at least 2 tiles, at most 1024 tiles
+    long long target = 4ll * ctx->sm_count;
+    long long n_ranges = (target + (long long)p.n_groups * n_prob - 1) / ((long long)p.n_groups * n_prob);
+    if (n_ranges < 1) n_ranges = 1;
+    long long range_tiles = (n_tiles + n_ranges - 1) / n_ranges;
+    if (range_tiles < 2) range_tiles = 2;
+    if (range_tiles > kMaxRangeTiles) range_tiles = kMaxRangeTiles;
+    if (range_tiles > n_tiles) range_tiles = n_tiles;
+    n_ranges = (n_tiles + range_tiles - 1) / range_tiles;
+    if ((long long)p.n_groups * n_ranges > 0x7FFFFFFFll || n_prob > 65535)
+        return slm_fail(SLM_ERR_UNSUPPORTED, "problem too large for one tensor-variant launch");
+    p.range_tiles = (int)range_tiles;
+    p.n_ranges = (int)n_ranges;
+
+    const size_t cand_bytes = (size_t)n_prob * (size_t)n_ranges * 2 * (size_t)p.nq * sizeof(float2);
+    SLM_TRY(slm_buf_reserve(ctx, &ctx->scratch, cand_bytes));
+    p.cand = reinterpret_cast<float2 *>(ctx->scratch.p);
+
+    SLM_TRY(slm_prof_begin(ctx, stream));
+    switch (p.mt) {
+    case 1: SLM_TRY(launch_tc<1>(p, n_prob, stream)); break;
+    case 2: SLM_TRY(launch_tc<2>(p, n_prob, stream)); break;
+    default: SLM_TRY(launch_tc<3>(p, n_prob, stream)); break;
+    }
+    SLM_TRY(slm_prof_end(ctx, stream));
+    const long long warps = (long long)n_prob * p.nq;   // one warp per (problem, query)
+    tc_refine_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p, base,
+                                                                     reinterpret_cast<unsigned long long *>(keys_out));
+    SLM_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    return SLM_OK;
+}
+
+}  // namespace
+
+int slm_tc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                     uint64_t *keys_out, cudaStream_t stream)
+{
+    TcParams p{};
+    p.q = q; p.t = t; p.desc = nullptr; p.pairs = nullptr; p.frame_words = 0;
+    p.nq = (int)nq; p.nt = (int)nt;
+    return tc_run(ctx, p, 1, base, keys_out, stream);
+}
+
+int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
+                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream)
+{
+    TcParams p{};
+    p.q = nullptr; p.t = nullptr; p.desc = desc; p.pairs = pairs_dev;
+    p.frame_words = n_per_frame * 8;
+    p.nq = (int)n_per_frame; p.nt = (int)n_per_frame;
+    return tc_run(ctx, p, (int)n_pairs, 0, keys_out, stream);
+}

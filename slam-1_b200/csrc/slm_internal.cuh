@@ -1,0 +1,107 @@
+// slm_internal.cuh -- shared declarations of libslammatch.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "slammatch.h"
+
+// Packed result key used between kernels: (distance << 32) | global train index.
+// Unsigned order of the key == OpenCV's (distance, trainIdx) order.
+static constexpr unsigned long long kKeyNone = 0xFFFFFFFFFFFFFFFFull;
+
+struct slm_buf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct slm_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int variant = SLM_VARIANT_AUTO;
+    int last_variant = 0;
+    int64_t launches = 0;
+    // device buffers owned by the ctx, each grown on demand (never shrunk)
+    slm_buf scratch;   // variant-internal partial results
+    slm_buf keys;      // forward packed keys
+    slm_buf rev;       // reverse-search packed keys (cross-check)
+    slm_buf misc;      // pair lists, expanded operands, ...
+    slm_buf io;        // device copies of host inputs / outputs (slm_knn2_host)
+    // pinned staging for host results
+    void *pin = nullptr;
+    size_t pin_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    // optional timing of the dominant kernel (slm_profile_enable)
+    int profile = 0;
+    static constexpr int kMaxProf = 4096;
+    cudaEvent_t *prof_ev = nullptr;   // 2 * kMaxProf events, created lazily
+    int prof_n = 0;
+};
+
+// Bracket the dominant kernel with events when profiling is on (no-ops otherwise).
+int slm_prof_begin(slm_ctx *ctx, cudaStream_t stream);
+int slm_prof_end(slm_ctx *ctx, cudaStream_t stream);
+
+// error plumbing (api.cu)
+int slm_fail(int code, const char *fmt, ...);
+#define SLM_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return slm_fail(SLM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                               \
+    } while (0)
+#define SLM_TRY(expr)                  \
+    do {                               \
+        int r__ = (expr);              \
+        if (r__ != SLM_OK) return r__; \
+    } while (0)
+
+// Grow `buf` to at least `bytes` (device-synchronises before freeing the old block, so kernels of
+// earlier calls that still use it have finished).
+int slm_buf_reserve(slm_ctx *ctx, slm_buf *buf, size_t bytes);
+
+// One problem = one (query set, train set) pair.  Batched calls pass several via device memory.
+struct slm_problem {
+    const uint32_t *q;   // uint32[nq][8]
+    const uint32_t *t;   // uint32[nt][8]
+    int nq;
+    int nt;
+    long long base;      // global index of train row 0
+};
+
+// ---- variant P: LOP3(XOR)+POPC on the integer pipe (knn2_popc.cu) --------------------------------
+// Single problem or a batch of equally-shaped problems (n_prob >= 1, pairs given by frame indices).
+// Writes packed keys uint64[n_prob][nq][2].
+int slm_popc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
+                       int64_t base, uint64_t *keys_out, cudaStream_t stream);
+int slm_popc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame,
+                               const int32_t *pairs_dev, int64_t n_pairs, uint64_t *keys_out,
+                               cudaStream_t stream);
+
+// ---- finalize / merge / compaction (finalize.cu) -------------------------------------------------
+// keys uint64[n][2] -> idx/dist/accept.  rev_keys (optional) = reverse search keys uint64[nt][2] used
+// for the cross-check; train_index_base is subtracted from the forward index to address it.
+int slm_finalize(slm_ctx *ctx, const uint64_t *keys, int64_t n, int32_t ratio_num, int32_t ratio_den,
+                 const uint64_t *rev_keys, int64_t nt, int64_t train_index_base, int32_t *idx_out,
+                 int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
+int slm_merge_keys(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int64_t nq,
+                   uint64_t *keys_out, cudaStream_t stream);
+int slm_compact(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
+                int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, cudaStream_t stream);
+
+// ---- variant T: +-1 fp8 expansion + tcgen05.mma with TMEM accumulators (knn2_tc.cu) ---------------
+int slm_tc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
+                     int64_t base, uint64_t *keys_out, cudaStream_t stream);
+int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
+                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream);
+
+// ---- variant B: b1 AND.POPC mma.sync tiles (knn2_bmma.cu; emulated by ptxas on sm_100a) -----------
+int slm_bmma_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
+                       int64_t base, uint64_t *keys_out, cudaStream_t stream);
+
+// ---- shape policy (dispatch.cu) -------------------------------------------------------------------
+int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
+                       int64_t base, uint64_t *keys_out, cudaStream_t stream);
+int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
+                          int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream);

@@ -1,0 +1,190 @@
+// tc_common.cuh -- sm_100a device helpers for variant T (tcgen05.mma + TMEM), hand-written PTX.
+//
+// The distance matrix of a (128 query) x (256 train) tile is a dense binary contraction.  Every
+// descriptor bit is expanded to an fp8 (e4m3) value +1.0 (bit 0) or -1.0 (bit 1); then
+//      dot(x, y) = #agreeing bits - #differing bits = 256 - 2 * Hamming(a, b)
+// so ONE tcgen05.mma chain (K = 256 = 8 instructions of K = 32) yields the Hamming distance as an
+// exact small integer in an fp32 TMEM accumulator -- no popc(a)+popc(b) correction terms.
+//
+// Shared-memory operand layout: K-major, SWIZZLE_NONE ("interleaved") canonical layout, 8-bit elements:
+//   core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes (row r at +16*r)
+//   LBO (leading byte offset) = distance between the two 16-byte K-chunks of one MMA      = 128 B
+//   SBO (stride  byte offset) = distance between consecutive 8-row groups along M / N     = 2048 B
+// i.e. an 8-row group is 2 KB: 16 K-chunks x 128 B.  Byte (row r, k) lives at
+//   (r / 8) * 2048 + (k / 16) * 128 + (r % 8) * 16 + (k % 16).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstdio>
+
+namespace tc {
+
+constexpr uint32_t kLBO = 128;
+constexpr uint32_t kSBO = 2048;
+constexpr uint32_t kRowGroupBytes = 2048;          // 8 rows x 256 expanded bytes
+constexpr uint32_t kFp8PlusOne = 0x38383838u;      // e4m3 +1.0 in every byte; bit 7 set => -1.0
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU (a hung box is a strike); trap instead.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag)
+{
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            printf("slammatch: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
+                   threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM allocation --------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot_in_smem, uint32_t ncols)   // whole warp
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
+                 "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)          // whole warp
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- descriptors -------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (64-bit): start address >> 4 in [0,14), LBO >> 4 in [16,30),
+// SBO >> 4 in [32,46), descriptor version 1 (Blackwell) in [46,48), layout type in [61,64) (0 = no swizzle).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo = kLBO, uint32_t sbo = kSBO)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// Instruction descriptor for kind::f8f6f4: D = F32 (bits [4,6) = 1), A = B = E4M3 (0), both K-major,
+// N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t idesc_e4m3_f32(uint32_t M, uint32_t N)
+{
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, one elected thread.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives when every tcgen05 op issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers ---------------------------------------------------------------------------
+// 32 lanes x 32 consecutive 32-bit columns: thread l of the warp gets lane (base_lane + l), columns
+// [col, col + 32).  The wait is fused so the registers are valid when the statement retires.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+// Same load without the wait (software pipelining); pair with tmem_ld_wait() + keep_alive().
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32])
+{
+    // the "+r" operands pin every consumer of v behind the wait in program order
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
+
+// ---- bit -> fp8 (+-1) expansion -----------------------------------------------------------------------
+// 4 descriptor bits (a clean nibble, value 0..15) -> 4 bytes: bit i lands on bit 7 of byte i via one
+// multiply (0x10204080 = 2^7 + 2^14 + 2^21 + 2^28; the 16 partial products hit distinct bit positions, so
+// there are no carries), then one LOP3 masks the sign bits and ORs in +1.0.
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t nib)
+{
+    return ((nib * 0x10204080u) & 0x80808080u) | kFp8PlusOne;
+}
+// One 32-bit descriptor word -> 32 expanded bytes = two 16-byte K-chunks.
+__device__ __forceinline__ void expand_word(uint32_t w, uint4 &lo, uint4 &hi)
+{
+    const uint32_t even = w & 0x0F0F0F0Fu;         // nibbles 0,2,4,6 in bytes 0..3
+    const uint32_t odd = (w >> 4) & 0x0F0F0F0Fu;   // nibbles 1,3,5,7
+    lo.x = expand_nibble(__byte_perm(even, 0, 0x4440));
+    lo.y = expand_nibble(__byte_perm(odd, 0, 0x4440));
+    lo.z = expand_nibble(__byte_perm(even, 0, 0x4441));
+    lo.w = expand_nibble(__byte_perm(odd, 0, 0x4441));
+    hi.x = expand_nibble(__byte_perm(even, 0, 0x4442));
+    hi.y = expand_nibble(__byte_perm(odd, 0, 0x4442));
+    hi.z = expand_nibble(__byte_perm(even, 0, 0x4443));
+    hi.w = expand_nibble(__byte_perm(odd, 0, 0x4443));
+}
+// Expand one 256-bit descriptor (8 words) into its row of a K-major no-swizzle operand tile.
+// `tile` = shared-memory byte address of the tile, `row` = row inside the tile.
+__device__ __forceinline__ void expand_row_to_smem(uint32_t tile, int row, const uint4 &d0, const uint4 &d1)
+{
+    const uint32_t base = tile + (uint32_t)(row >> 3) * kRowGroupBytes + (uint32_t)(row & 7) * 16;
+    const uint32_t w[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint4 lo, hi;
+        expand_word(w[i], lo, hi);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (2 * i) * kLBO), "r"(lo.x), "r"(lo.y),
+                     "r"(lo.z), "r"(lo.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (2 * i + 1) * kLBO), "r"(hi.x), "r"(hi.y),
+                     "r"(hi.z), "r"(hi.w) : "memory");
+    }
+}
+
+}  // namespace tc

@@ -1,0 +1,15 @@
+"""slammatch -- B200-native exact Hamming kNN-2 matching of 256-bit ORB descriptors.
+
+Drop-in for the matcher object of the DavidHan008/SLAM-1 pipeline (tracking.py:12-34,
+keypoint.py:35-57, Point3D.py:33-52): ``slammatch.Matcher`` mirrors the cv2 ``DescriptorMatcher``
+members the reference uses, ``slammatch.install()`` rebinds ``cv2.FlannBasedMatcher`` so the unmodified
+reference runs on the GPU, ``slammatch.knn2`` is the array fast path.  All arithmetic lives in
+libslammatch.so (hand-written CUDA for sm_100a behind the C-ABI of include/slammatch.h).
+"""
+from . import synth  # noqa: F401  (pure numpy; safe without a GPU)
+from ._lib import SlamMatchError, Context, context, load, LIB_PATH, SYMBOLS, VARIANTS  # noqa: F401
+from .matcher import (DMatch, Matcher, REFERENCE_RATIO, get_matches, good_matches, install, knn2,  # noqa: F401
+                      uninstall)
+
+__all__ = ["Matcher", "DMatch", "knn2", "install", "uninstall", "get_matches", "good_matches", "context",
+           "Context", "SlamMatchError", "load", "synth", "REFERENCE_RATIO"]

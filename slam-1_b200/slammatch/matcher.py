@@ -1,0 +1,266 @@
+"""Host-side mirror of the reference's matcher interface (the Python side of the drop-in boundary).
+
+Reference call sites (relative to /root/reference):
+    flann = cv2.FlannBasedMatcher(indexParams=..., searchParams=...)   tracking.py:14-17  keypoint.py:40-43  Point3D.py:35-39
+    matches = flann.knnMatch(des1, des2, k=2)                          tracking.py:22     keypoint.py:44     Point3D.py:40
+    for m, n in matches: if m.distance < 0.7 * n.distance: ...         tracking.py:24-30  keypoint.py:45-51  Point3D.py:41-49
+
+``Matcher`` keeps those names, argument meanings, return layout (tuple of rows of ``DMatch`` with
+``queryIdx / trainIdx / imgIdx / distance``; rows have min(k, nt) entries so the reference's swallowed
+``ValueError`` on short rows behaves identically) and error behaviour (dtype / column checks raise, empty
+inputs give empty rows).  The arithmetic runs in libslammatch.so on a B200; results equal the exhaustive
+``cv2.BFMatcher(cv2.NORM_HAMMING)`` bit for bit (SURVEY.md D1 explains why the approximate LSH matcher
+itself cannot be an oracle).
+
+``knn2`` is the array fast path (numpy in / numpy out through ``slm_knn2_host``, or torch CUDA tensors
+in / out through ``slm_knn2_filter`` with no copies).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+try:  # real cv2.DMatch objects when OpenCV is importable (it is wherever the reference runs)
+    import cv2 as _cv2
+    _DMatch = _cv2.DMatch
+except Exception:  # pragma: no cover - cv2 is present in the supported images
+    _cv2 = None
+
+    class _DMatch:  # minimal stand-in with the four fields the reference reads
+        __slots__ = ("queryIdx", "trainIdx", "imgIdx", "distance")
+
+        def __init__(self, queryIdx=-1, trainIdx=-1, imgIdx=-1, distance=float("inf")):
+            self.queryIdx, self.trainIdx, self.imgIdx, self.distance = queryIdx, trainIdx, imgIdx, float(distance)
+
+DMatch = _DMatch
+REFERENCE_RATIO = (7, 10)   # the literal 0.7 at tracking.py:27, keypoint.py:48, Point3D.py:44
+
+
+def _as_desc(a, name):
+    """uint8[n, 32] C-contiguous, as orb.py:23-24 produces; OpenCV asserts on dtype / column mismatch."""
+    if a is None:
+        raise ValueError(f"{name} is None")
+    a = np.asarray(a)
+    if a.size == 0:
+        return np.zeros((0, 32), dtype=np.uint8)
+    if a.dtype != np.uint8:
+        raise ValueError(f"{name}: dtype must be uint8 (ORB descriptors), got {a.dtype}")
+    if a.ndim != 2 or a.shape[1] != 32:
+        raise ValueError(f"{name}: shape must be [n, 32] (256-bit descriptors), got {a.shape}")
+    return np.ascontiguousarray(a)
+
+
+def _ratio_args(ratio):
+    if ratio is None:
+        return 0, 1
+    num, den = int(ratio[0]), int(ratio[1])
+    if num <= 0 or den <= 0:
+        raise ValueError("ratio must be a pair of positive integers (num, den)")
+    return num, den
+
+
+def _is_torch_cuda(x) -> bool:
+    return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
+
+
+def knn2(q, t, ratio=REFERENCE_RATIO, cross_check: bool = False, device: int | None = None,
+         train_index_base: int = 0, variant: str | None = None):
+    """Exact Hamming 2-NN of every row of ``q`` in ``t`` + Lowe ratio (+ cross-check).
+
+    Returns ``idx int32[nq, 2]``, ``dist int32[nq, 2]``, ``accept uint8[nq]`` -- numpy arrays for numpy
+    inputs, CUDA tensors for CUDA-tensor inputs.  ``ratio=(num, den)`` is the integer form of the
+    reference's ``m.distance < r * n.distance``; ``None`` disables it.
+    """
+    num, den = _ratio_args(ratio)
+    if _is_torch_cuda(q) or _is_torch_cuda(t):
+        return _knn2_device(q, t, num, den, cross_check, train_index_base, variant)
+    q = _as_desc(q, "queryDescriptors")
+    t = _as_desc(t, "trainDescriptors")
+    ctx = _lib.context(0 if device is None else device)
+    if variant is not None:
+        ctx.set_variant(variant)
+    nq, nt = q.shape[0], t.shape[0]
+    idx = np.full((nq, 2), -1, dtype=np.int32)
+    dist = np.full((nq, 2), -1, dtype=np.int32)
+    acc = np.zeros(nq, dtype=np.uint8)
+    if nq:
+        _lib.check(ctx.lib.slm_knn2_host(ctx.handle, q.ctypes.data, nq, t.ctypes.data if nt else None, nt,
+                                         num, den, int(bool(cross_check)), idx.ctypes.data, dist.ctypes.data,
+                                         acc.ctypes.data))
+        if train_index_base:
+            idx[idx >= 0] += train_index_base
+    return idx, dist, acc
+
+
+def _dev_desc(x, name):
+    import torch
+    if not _is_torch_cuda(x):
+        raise ValueError(f"{name}: mixing host and device inputs is not supported")
+    if x.dtype == torch.uint8 and x.dim() == 2 and x.shape[1] == 32:
+        pass
+    elif x.dtype == torch.int32 and x.dim() == 2 and x.shape[1] == 8:
+        pass  # packed uint32x8 view of the same bytes
+    else:
+        raise ValueError(f"{name}: expected uint8[n,32] or int32[n,8] CUDA tensor, got {x.dtype} {tuple(x.shape)}")
+    return x.contiguous()
+
+
+def _knn2_device(q, t, num, den, cross_check, base, variant):
+    import torch
+    q = _dev_desc(q, "queryDescriptors")
+    t = _dev_desc(t, "trainDescriptors")
+    dev = q.device
+    ctx = _lib.context(dev.index or 0)
+    if variant is not None:
+        ctx.set_variant(variant)
+    nq, nt = q.shape[0], t.shape[0]
+    idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+    dist = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+    acc = torch.empty((nq,), dtype=torch.uint8, device=dev)
+    if nq:
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(ctx.lib.slm_knn2_filter(ctx.handle, q.data_ptr(), nq, t.data_ptr() if nt else None, nt, int(base),
+                                           num, den, int(bool(cross_check)), idx.data_ptr(), dist.data_ptr(),
+                                           acc.data_ptr(), stream))
+    return idx, dist, acc
+
+
+class Matcher:
+    """Drop-in for the object built by ``cv2.FlannBasedMatcher(indexParams=..., searchParams=...)``.
+
+    The LSH parameters are accepted and ignored (the search is exhaustive and exact).  Only the
+    ``DescriptorMatcher`` members on or next to the reference's path are provided: ``knnMatch``,
+    ``match``, ``add`` / ``clear`` / ``getTrainDescriptors`` / ``empty``.
+    """
+
+    def __init__(self, indexParams=None, searchParams=None, *, crossCheck: bool = False, device: int = 0,
+                 variant: str | None = None):
+        self.indexParams, self.searchParams = indexParams, searchParams
+        self.crossCheck = bool(crossCheck)
+        self.device = device
+        self.variant = variant
+        self._train: list[np.ndarray] = []
+
+    # -- train collection (OpenCV's add([...]) + knnMatch(q, k) form) --------------------------------
+    def add(self, descriptors):
+        for d in descriptors:
+            self._train.append(_as_desc(d, "descriptors"))
+
+    def clear(self):
+        self._train = []
+
+    def empty(self) -> bool:
+        return not self._train
+
+    def getTrainDescriptors(self):
+        return list(self._train)
+
+    def train(self):  # nothing to build: the search is exhaustive
+        return None
+
+    def _collection(self):
+        sizes = np.array([d.shape[0] for d in self._train], dtype=np.int64)
+        flat = np.concatenate(self._train, axis=0) if self._train else np.zeros((0, 32), np.uint8)
+        return flat, np.concatenate([[0], np.cumsum(sizes)])
+
+    # -- the hot path ----------------------------------------------------------------------------
+    def knnMatch(self, queryDescriptors, trainDescriptors=None, k: int = 2, mask=None, compactResult: bool = False):
+        """``matcher.knnMatch(des1, des2, k=2)`` (tracking.py:22): tuple[nq] of tuple[min(k, nt)] of DMatch."""
+        if mask is not None:
+            raise NotImplementedError("mask= is not on the reference's path and is not supported")
+        if isinstance(trainDescriptors, (int, np.integer)) and k == 2:  # knnMatch(q, k) positional form
+            trainDescriptors, k = None, int(trainDescriptors)
+        if k not in (1, 2):
+            raise ValueError("only k=1 and k=2 are supported (the reference uses k=2)")
+        if self.crossCheck and k != 1:
+            # OpenCV: batch_distance.cpp:303 asserts K == 1 when crossCheck is set
+            raise ValueError("crossCheck=True requires k == 1 (as in OpenCV); use knn2(cross_check=True) for kNN-2 + cross-check")
+        q = _as_desc(queryDescriptors, "queryDescriptors")
+        if trainDescriptors is None:
+            t, offsets = self._collection()
+        else:
+            t, offsets = _as_desc(trainDescriptors, "trainDescriptors"), None
+        idx, dist, acc = knn2(q, t, ratio=None, cross_check=self.crossCheck, device=self.device, variant=self.variant)
+        return self._rows(idx, dist, acc if self.crossCheck else None, k, offsets)
+
+    def match(self, queryDescriptors, trainDescriptors=None, mask=None):
+        """Best neighbour per query as a flat list (``DescriptorMatcher.match``); honours crossCheck."""
+        rows = self.knnMatch(queryDescriptors, trainDescriptors, k=1, mask=mask)
+        return [r[0] for r in rows if r]
+
+    @staticmethod
+    def _rows(idx, dist, keep, k, offsets):
+        out = []
+        idx_l, dist_l = idx.tolist(), dist.tolist()
+        keep_l = keep.tolist() if keep is not None else None
+        if offsets is not None:
+            img_all = np.searchsorted(offsets, np.maximum(idx, 0), side="right") - 1
+            loc_all = (idx - offsets[img_all]).tolist()
+            img_l = img_all.tolist()
+        for i, (ii, dd) in enumerate(zip(idx_l, dist_l)):
+            row = []
+            if keep_l is None or keep_l[i]:
+                for c in range(k):
+                    if ii[c] < 0:
+                        break
+                    if offsets is None:
+                        row.append(DMatch(i, ii[c], 0, float(dd[c])))
+                    else:
+                        row.append(DMatch(i, loc_all[i][c], img_l[i][c], float(dd[c])))
+            out.append(tuple(row))
+        return tuple(out)
+
+
+# ---- the verified seam: rebind cv2.FlannBasedMatcher -------------------------
+_saved = {}
+
+
+def install(cv2_module=None, also_bfmatcher: bool = False):
+    """Make the UNMODIFIED reference use this matcher: ``cv2.FlannBasedMatcher = slammatch.Matcher``.
+
+    tracking.get_matches, keypoint.track_keypoints_left_to_right_new and
+    Point3D.find_2D_and_3D_correspondenses all construct the matcher through that name on every call.
+    """
+    mod = cv2_module or _cv2
+    if mod is None:
+        raise RuntimeError("cv2 is not importable; pass the module the reference uses")
+    if "FlannBasedMatcher" not in _saved:
+        _saved["FlannBasedMatcher"] = mod.FlannBasedMatcher
+    mod.FlannBasedMatcher = Matcher
+    if also_bfmatcher:
+        if "BFMatcher" not in _saved:
+            _saved["BFMatcher"] = mod.BFMatcher
+
+        def _bf(normType=None, crossCheck=False):
+            return Matcher(crossCheck=crossCheck)
+        mod.BFMatcher = _bf
+    return mod
+
+
+def uninstall(cv2_module=None):
+    mod = cv2_module or _cv2
+    for name, obj in list(_saved.items()):
+        setattr(mod, name, obj)
+        del _saved[name]
+
+
+# ---- array-level mirrors of the three reference helpers (no DMatch objects, no Python loops) ---------
+def good_matches(des1, des2, ratio=REFERENCE_RATIO, device: int = 0):
+    """The ``good`` list of tracking.py:24-30 as arrays: (queryIdx, trainIdx, distance) of accepted rows,
+    truncated at the first row with fewer than two neighbours exactly like the swallowed ValueError."""
+    idx, dist, acc = knn2(des1, des2, ratio=ratio, device=device)
+    short = np.nonzero(idx[:, 1] < 0)[0]
+    stop = int(short[0]) if short.size else idx.shape[0]
+    rows = np.nonzero(acc[:stop])[0]
+    return rows, idx[rows, 0], dist[rows, 0]
+
+
+def get_matches(kp1_pts, des1, kp2_pts, des2, device: int = 0):
+    """tracking.get_matches (tracking.py:12-34) with keypoint coordinates given as float arrays."""
+    rows, tidx, _ = good_matches(des1, des2, device=device)
+    q1 = np.float32(np.asarray(kp1_pts)[rows])
+    q2 = np.float32(np.asarray(kp2_pts)[tidx])
+    return q1, q2

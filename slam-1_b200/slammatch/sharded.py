@@ -1,0 +1,101 @@
+"""Train-set sharding over the GPUs of one box (BASELINE configs 4 and 5).
+
+The keyframe-descriptor database (config 5) or the visual vocabulary (config 4) is split into contiguous
+row blocks, one per rank; the query batch is replicated.  Every rank runs the single-GPU kernel on its
+block with ``train_index_base`` = first global row and emits packed top-2 keys
+``(distance << 32) | global index``; ONE all-gather of ``nq x 2`` keys per rank (NCCL over NVLink) is the
+only exchange step, followed by a merge kernel that keeps the two smallest keys -- unsigned key order is
+OpenCV's ``(distance, imgIdx, trainIdx)`` collection order, so the result is byte-identical for any
+shard count.  Frame-to-frame / local-map matching (configs 1-3) never shards.
+
+The reference has no counterpart (loop_closure.py:7-36 matches two frames; place_recognition.py is
+empty): this module only defines how the existing kernel scales.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+
+def shard_bounds(n_rows: int, world_size: int):
+    """Contiguous, near-equal row blocks: [(first, last_exclusive)] per rank (32-row aligned interior cuts)."""
+    if world_size <= 0:
+        raise ValueError("world_size must be positive")
+    cuts = [0]
+    for r in range(1, world_size):
+        c = (n_rows * r) // world_size
+        c -= c % 32
+        cuts.append(max(c, cuts[-1]))
+    cuts.append(n_rows)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
+class ShardedMatcher:
+    """One rank's view of a sharded train set.
+
+    ``local_keys(q) -> int64[nq, 2]`` and ``merge(gathered int64[W, nq, 2]) -> result`` default to the CUDA
+    entry points (slm_knn2_keys / slm_merge_top2); tests inject CPU stand-ins to exercise the collective
+    plumbing under gloo.
+    """
+
+    def __init__(self, train_shard, first_row: int, group=None, ratio=(7, 10), variant: Optional[str] = None,
+                 local_keys: Optional[Callable] = None, merge: Optional[Callable] = None):
+        import torch.distributed as dist
+        self.train = train_shard
+        self.first_row = int(first_row)
+        self.group = group
+        self.ratio = ratio
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self._local_keys = local_keys or self._cuda_local_keys
+        self._merge = merge or self._cuda_merge
+        self._variant = variant
+        self._gather_buf = None
+
+    # -- CUDA implementations ---------------------------------------------------------------------
+    def _ctx(self):
+        from . import _lib
+        ctx = _lib.context(self.train.device.index or 0)
+        if self._variant is not None:
+            ctx.set_variant(self._variant)
+        return ctx
+
+    def _cuda_local_keys(self, q):
+        import torch
+        from . import _lib
+        ctx = self._ctx()
+        nq, nt = q.shape[0], self.train.shape[0]
+        keys = torch.empty((nq, 2), dtype=torch.int64, device=q.device)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        _lib.check(ctx.lib.slm_knn2_keys(ctx.handle, q.data_ptr(), nq, self.train.data_ptr() if nt else None, nt,
+                                         self.first_row, keys.data_ptr(), stream))
+        return keys
+
+    def _cuda_merge(self, gathered):
+        import torch
+        from . import _lib
+        ctx = self._ctx()
+        w, nq, _ = gathered.shape
+        dev = gathered.device
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        dist_ = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        acc = torch.empty((nq,), dtype=torch.uint8, device=dev)
+        num, den = self.ratio if self.ratio is not None else (0, 1)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(ctx.lib.slm_merge_top2(ctx.handle, gathered.data_ptr(), w, nq, int(num), int(den), idx.data_ptr(),
+                                          dist_.data_ptr(), acc.data_ptr(), stream))
+        return idx, dist_, acc
+
+    # -- the sharded query ----------------------------------------------------------------------------
+    def knn2(self, q):
+        """Local top-2 keys -> all-gather -> merge.  Every rank returns the full, identical result."""
+        import torch
+        import torch.distributed as dist
+        keys = self._local_keys(q)
+        if self.world > 1:
+            shape = (self.world,) + tuple(keys.shape)
+            if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or self._gather_buf.device != keys.device:
+                self._gather_buf = torch.empty(shape, dtype=keys.dtype, device=keys.device)
+            dist.all_gather_into_tensor(self._gather_buf, keys.contiguous(), group=self.group)
+            gathered = self._gather_buf
+        else:
+            gathered = keys.reshape((1,) + tuple(keys.shape))
+        return self._merge(gathered)
