@@ -352,13 +352,22 @@ def ours(args, w, cfg_id):
             # one comparison = a 256-term dot product of +-1 fp8 values = 512 flop on the tcgen05 pipe
             ach = cmp_per_launch * 512 / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
             bf16 = peaks.get("bf16_tflops", 1590.0)
-            peak = 2.0 * bf16
+            probe = {}
+            try:
+                probe = json.load(open(os.path.join(ROOT, "profiles", "peaks_probe.json")))
+            except Exception:
+                pass
+            # The kernel issues tcgen05.mma kind::f8f6f4 (2x the bf16 rate).  MEASURED_PEAKS.json only holds a
+            # cuBLAS bf16 figure, so the denominator is the HIGHER of 2 x that figure and this repo's own
+            # back-to-back tcgen05 fp8 probe on the same pool (profiles/r1_tc_probe_v1.txt).
+            peak = max(2.0 * bf16, probe.get("tcgen05_f8f6f4_tflops_burst", 0.0))
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": (ach / peak) if ach else None, "traffic": None,
                     "kernel": "knn2_tc_kernel", "kernel_ms": kern_avg_ms,
-                    "peak_note": ("2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json: %.1f TF/s): kind::f8f6f4 issues at "
-                                  "twice the bf16 rate" % bf16) if peaks else "2 x fallback bf16 1590 TF/s",
-                    "frac_vs_bf16_measured": (ach / bf16) if ach else None,
+                    "peak_note": ("max(2 x measured cuBLAS bf16 burst %.1f TF/s [%s], own tcgen05 kind::f8f6f4 probe %.1f TF/s)"
+                                  % (bf16, "MEASURED_PEAKS.json" if peaks else "fallback",
+                                     probe.get("tcgen05_f8f6f4_tflops_burst", 0.0))),
+                    "frac_vs_2x_bf16_measured": (ach / (2.0 * bf16)) if ach else None,
                     "algorithmic_unit": "1 cmp = 512 fp8 flop (256-bit +-1 dot product)"}
         else:
             # integer pipe: 8 POPC32 per comparison; peak from the micro-benchmark (profiles/), 16 POPC/clk/SM nominal

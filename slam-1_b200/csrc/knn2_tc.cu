@@ -57,7 +57,7 @@ struct TcParams {
     int mt;                       // query tiles per group (1..kMaxMT)
     int n_groups;                 // ceil(nq / (128 * mt))
     int range_tiles, n_ranges;
-    float2 *cand;                 // [n_prob][n_ranges][2][nq]: best two chunk keys per epilogue set
+    float2 *cand;                 // [n_prob][nq][n_ranges][2 sets]: best two chunk keys per epilogue set
 };
 
 struct TcBarriers {
@@ -142,28 +142,53 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(TcParams p)
                     const int ab = job & 1;
                     tc::mbar_wait(&bars->acc_full[ab], (job >> 1) & 1, 10 + ab);
                     tc::tc_fence_after();
+                    const uint32_t acc_addr = lane_addr + ab * kTileN + set * kChunk;
+                    if (n_chunks == kChunksPerTile) {
+                        // full tile: 4 chunks per warp, TMEM load of chunk i+1 in flight while chunk i is reduced
+                        uint32_t va[32], vb[32];
+                        tc::tmem_ld32_nowait(acc_addr, va);
 #pragma unroll
-                    for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
-                        const int c = 2 * cc + set;
-                        if (c < n_chunks) {
-                            uint32_t v[32];
-                            tc::tmem_ld32(lane_addr + ab * kTileN + c * kChunk, v);
-                            const float key = fmaf(max32(v), kKeyScale, chunk_bias - (float)c);
+                        for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
+                            uint32_t (&cur)[32] = (cc & 1) ? vb : va;
+                            uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+                            tc::tmem_ld_wait(cur);
+                            if (cc + 1 < kChunksPerTile / 2) {
+                                tc::tmem_ld32_nowait(acc_addr + (cc + 1) * 2 * kChunk, nxt);
+                            } else {
+                                // every load of this accumulator has landed: hand it back before the last reduce
+                                tc::tc_fence_before();
+                                tc::mbar_arrive(&bars->acc_empty[ab]);
+                            }
+                            const float key = fmaf(max32(cur), kKeyScale, chunk_bias - (float)(2 * cc + set));
                             b2[m] = fmaxf(b2[m], fminf(b1[m], key));
                             b1[m] = fmaxf(b1[m], key);
                         }
+                    } else {
+                        // last, partial tile of the train set: only chunks that contain valid columns count
+#pragma unroll
+                        for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
+                            const int c = 2 * cc + set;
+                            if (c < n_chunks) {
+                                uint32_t v[32];
+                                tc::tmem_ld32(acc_addr + cc * 2 * kChunk, v);
+                                const float key = fmaf(max32(v), kKeyScale, chunk_bias - (float)c);
+                                b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                                b1[m] = fmaxf(b1[m], key);
+                            }
+                        }
+                        tc::tc_fence_before();
+                        tc::mbar_arrive(&bars->acc_empty[ab]);
                     }
-                    tc::tc_fence_before();
-                    tc::mbar_arrive(&bars->acc_empty[ab]);
                     ++job;
                 }
             }
         }
-        float2 *cand = p.cand + (((long long)blockIdx.y * p.n_ranges + range) * 2 + set) * (long long)p.nq;
+        // candidates of one query are contiguous: cand[prob][query][range][set] (float2 = best two chunk keys)
+        float2 *cand = p.cand + (long long)blockIdx.y * p.nq * p.n_ranges * 2 + (long long)range * 2 + set;
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
             const int qi = q_first + m * kTileM + quad * 32 + lane;
-            if (m < mt_here && qi < p.nq) cand[qi] = make_float2(b1[m], b2[m]);
+            if (m < mt_here && qi < p.nq) cand[(long long)qi * p.n_ranges * 2] = make_float2(b1[m], b2[m]);
         }
     } else if (warp < kEpiWarps + kExpWarps) {
         // ===================== expanders: packed bits -> +-1 fp8 operand tiles =====================
@@ -239,8 +264,21 @@ __device__ __forceinline__ void top2_insert(unsigned long long &k1, unsigned lon
     k2 = min(k2, m);
 }
 
-// One warp per (problem, query).  Candidate chunk keys are decoded, the 32 rows of every candidate chunk
-// are re-scored with XOR+POPC (one row per lane) and reduced to the exact top-2 by (distance, index).
+__device__ __forceinline__ void top2_insert_max(unsigned long long &k1, unsigned long long &k2, unsigned long long key)
+{
+    unsigned long long m = min(k1, key);
+    k1 = max(k1, key);
+    k2 = max(k2, m);
+}
+
+// One warp per (problem, query).
+//   phase 1: reduce the query's candidate chunk keys (2 per epilogue set per range) to the best two chunks of
+//            the whole train set by (max dot desc, global chunk index asc).  The exact top-2 rows lie inside
+//            them: the nearest row's chunk has the largest chunk maximum (lowest chunk on ties, because the
+//            row has the lowest index among its ties); the runner-up is either in the same chunk or is the
+//            best row outside it, which by the same argument is in the second-best chunk.
+//   phase 2: re-score those 64 rows with XOR+POPC (one row per lane and chunk) and keep the exact top-2 by
+//            (distance, global index) -- the reference tie-break.
 __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long base, unsigned long long *keys_out)
 {
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -255,37 +293,41 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
         q = p.desc + (long long)pr.x * p.frame_words;
         t = p.desc + (long long)pr.y * p.frame_words;
     }
+    // phase 1
+    const int n_cand = p.n_ranges * 4;   // (range, set, slot)
+    const float *cand = reinterpret_cast<const float *>(p.cand) + gw * (long long)n_cand;
+    const int chunks_per_range = p.range_tiles * kChunksPerTile;
+    unsigned long long c1 = 0, c2 = 0;   // 0 = none; key = (dot + 257) << 32 | ~global_chunk
+    for (int ci = lane; ci < n_cand; ci += 32) {
+        const float key = cand[ci];
+        if (key > -1.0e30f) {
+            const int ki = (int)key + 256 * 8192;
+            const unsigned gchunk = (unsigned)((ci >> 2) * chunks_per_range + (8191 - (ki & 8191)));
+            top2_insert_max(c1, c2, ((unsigned long long)((ki >> 13) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, c1, o);
+        const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+        top2_insert_max(c1, c2, o1);
+        top2_insert_max(c1, c2, o2);
+    }
+    // phase 2
     const uint4 *qs = reinterpret_cast<const uint4 *>(q + (long long)qi * 8);
     const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
-
     unsigned long long k1 = kKeyNone, k2 = kKeyNone;
-    const int n_cand = p.n_ranges * 4;   // (range, set, slot)
-    const float *cand = reinterpret_cast<const float *>(p.cand) + (long long)prob * p.n_ranges * 4 * (long long)p.nq;
-    for (int c0 = 0; c0 < n_cand; c0 += 32) {
-        // each lane fetches one candidate key, then the warp walks them together
-        int my_col = -1;
-        const int ci = c0 + lane;
-        if (ci < n_cand) {
-            const int r = ci >> 2, set = (ci >> 1) & 1, slot = ci & 1;
-            const float key = cand[(((long long)r * 2 + set) * p.nq + qi) * 2 + slot];
-            if (key > -1.0e30f) {
-                const int ki = (int)key + 256 * 8192;
-                const int chunk = 8191 - (ki & 8191);
-                my_col = (r * p.range_tiles * kTileN) + chunk * kChunk;
-            }
-        }
-        const int n_here = min(32, n_cand - c0);
-        for (int j = 0; j < n_here; ++j) {
-            const int col = __shfl_sync(0xFFFFFFFFu, my_col, j);
-            if (col < 0) continue;
-            const int row = col + lane;
-            if (row < p.nt) {
-                const uint4 *ts = reinterpret_cast<const uint4 *>(t + (long long)row * 8);
-                const uint4 ta = __ldg(ts), tb = __ldg(ts + 1);
-                const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
-                                   __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
-                top2_insert(k1, k2, ((unsigned long long)d << 32) | (unsigned long long)(base + row));
-            }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const unsigned long long c = s == 0 ? c1 : c2;
+        if (c == 0) continue;
+        const long long row = (long long)(0xFFFFFFFFu - (unsigned)(c & 0xFFFFFFFFull)) * kChunk + lane;
+        if (row < p.nt) {
+            const uint4 *ts = reinterpret_cast<const uint4 *>(t + row * 8);
+            const uint4 ta = __ldg(ts), tb = __ldg(ts + 1);
+            const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                               __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+            top2_insert(k1, k2, ((unsigned long long)d << 32) | (unsigned long long)(base + row));
         }
     }
 #pragma unroll

@@ -149,26 +149,26 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32])
 }
 
 // ---- bit -> fp8 (+-1) expansion -----------------------------------------------------------------------
-// 4 descriptor bits (a clean nibble, value 0..15) -> 4 bytes: bit i lands on bit 7 of byte i via one
-// multiply (0x10204080 = 2^7 + 2^14 + 2^21 + 2^28; the 16 partial products hit distinct bit positions, so
-// there are no carries), then one LOP3 masks the sign bits and ORs in +1.0.
-__device__ __forceinline__ uint32_t expand_nibble(uint32_t nib)
+// The contraction index K may be permuted freely as long as both operands use the same permutation, so
+// the expansion picks the cheapest bit -> byte mapping: output word k of a 32-bit descriptor word w is
+//      ((w << k) & 0x80808080) | 0x38383838          k = 0..7
+// i.e. bits {7-k, 15-k, 23-k, 31-k} of w land on the sign bits of the four e4m3 bytes (+1.0 = 0x38,
+// -1.0 = 0xB8).  One shift + one LOP3 per 4 output bytes.
+__device__ __forceinline__ uint32_t expand_shifted(uint32_t x)
 {
-    return ((nib * 0x10204080u) & 0x80808080u) | kFp8PlusOne;
+    return (x & 0x80808080u) | kFp8PlusOne;
 }
 // One 32-bit descriptor word -> 32 expanded bytes = two 16-byte K-chunks.
 __device__ __forceinline__ void expand_word(uint32_t w, uint4 &lo, uint4 &hi)
 {
-    const uint32_t even = w & 0x0F0F0F0Fu;         // nibbles 0,2,4,6 in bytes 0..3
-    const uint32_t odd = (w >> 4) & 0x0F0F0F0Fu;   // nibbles 1,3,5,7
-    lo.x = expand_nibble(__byte_perm(even, 0, 0x4440));
-    lo.y = expand_nibble(__byte_perm(odd, 0, 0x4440));
-    lo.z = expand_nibble(__byte_perm(even, 0, 0x4441));
-    lo.w = expand_nibble(__byte_perm(odd, 0, 0x4441));
-    hi.x = expand_nibble(__byte_perm(even, 0, 0x4442));
-    hi.y = expand_nibble(__byte_perm(odd, 0, 0x4442));
-    hi.z = expand_nibble(__byte_perm(even, 0, 0x4443));
-    hi.w = expand_nibble(__byte_perm(odd, 0, 0x4443));
+    lo.x = expand_shifted(w);
+    lo.y = expand_shifted(w << 1);
+    lo.z = expand_shifted(w << 2);
+    lo.w = expand_shifted(w << 3);
+    hi.x = expand_shifted(w << 4);
+    hi.y = expand_shifted(w << 5);
+    hi.z = expand_shifted(w << 6);
+    hi.w = expand_shifted(w << 7);
 }
 // Expand one 256-bit descriptor (8 words) into its row of a K-major no-swizzle operand tile.
 // `tile` = shared-memory byte address of the tile, `row` = row inside the tile.

@@ -148,10 +148,13 @@ def test_shard_count_invariance_through_merge(variant):
         assert np.array_equal(keys.cpu().numpy().view(np.uint64), ok), shards
 
 
-def test_batched_pairs_config3_shape():
+@pytest.mark.parametrize("n", [300, 777])
+def test_batched_pairs_config3_shape(n, variant):
     """Config 3 in miniature: all unordered frame pairs (i<j) of a keyframe batch in one call."""
     import torch
-    frames, n = 6, 300
+    if variant == "bmma":
+        pytest.skip("batched entry point runs the popc or tensor variant")
+    frames = 6
     rng = np.random.default_rng(5)
     base = synth.uniform(n, 50)
     desc = np.stack([base ^ np.packbits(rng.random((n, 256)) < 0.05 * (f + 1), axis=1, bitorder="little")
@@ -163,6 +166,7 @@ def test_batched_pairs_config3_shape():
     dist = torch.empty((P, n, 2), dtype=torch.int32, device="cuda")
     acc = torch.empty((P, n), dtype=torch.uint8, device="cuda")
     ctx = slammatch.context(0)
+    ctx.set_variant(variant)
     slammatch._lib.check(ctx.lib.slm_knn2_batched(ctx.handle, dd.data_ptr(), frames, n, pairs.ctypes.data, P, 7, 10,
                                                   idx.data_ptr(), dist.data_ptr(), acc.data_ptr(), None))
     torch.cuda.synchronize()
