@@ -4,6 +4,7 @@
 // There is no CPU implementation behind any entry point: without a CUDA device they fail.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -159,6 +160,7 @@ int slm_create(int device, slm_ctx **ctx_out)
     if (!ctx) return slm_fail(SLM_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->force_1cta = getenv("SLM_TC_1CTA") != nullptr;   // A/B switch: single-CTA tcgen05 kernel only
     SLM_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming));

@@ -256,6 +256,215 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(TcParams p)
     if (warp == kEpiWarps + kExpWarps) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// =====================================================================================================
+// 2-CTA variant (cta_group::2).  A CTA pair (cluster of 2, same TPC) works on one train range; each CTA
+// owns up to MT query tiles (its 128 rows of the M = 256 MMA) and expands / stores only HALF of every
+// 256-row train tile (CTA rank r holds tile rows [128 r, 128 r + 128)).  The leader CTA's elected thread
+// issues tcgen05.mma.cta_group::2; the hardware exchanges the B halves between the two SMs, so per SM the
+// MMA reads 8 KB of shared memory per instruction instead of 12 KB and the expansion work per SM halves.
+// (ncu on the 1-CTA kernel: tensor pipe 52 % active with the shared-memory data pipe ~85 % busy -- the
+// SS-mode operand fetch of an fp8 K=256 job is shared-memory-bandwidth bound on one SM.)
+// Barriers: "full" barriers live in the leader and collect arrivals from both CTAs (remote arrives);
+// "empty"/"acc_full" barriers are signalled into both CTAs by multicast tcgen05.commit.
+// =====================================================================================================
+constexpr int kExp2Warps = 4;
+constexpr int kExp2Threads = kExp2Warps * 32;                 // 128 = rows of a B half tile
+constexpr int kThreads2 = kEpiThreads + kExp2Threads + 32;    // 416
+constexpr uint32_t kBHalfBytes = 128 * 256;                   // 32 KB
+constexpr int kBStages2 = 3;
+constexpr int kMaxMT2 = 4;
+
+struct TcBarriers2 {
+    uint64_t a_full;
+    uint64_t b_full[kBStages2], b_empty[kBStages2];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int MT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_tc2_kernel(TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sA = smem;                                   // MT tiles of 32 KB
+    uint8_t *sB = smem + MT * kATileBytes;                // kBStages2 half tiles of 32 KB
+    TcBarriers2 *bars = reinterpret_cast<TcBarriers2 *>(smem + MT * kATileBytes + kBStages2 * kBHalfBytes);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = tc::cluster_ctarank();          // 0 = leader
+    const int item = blockIdx.x >> 1;                     // cluster index
+    const int n_gpairs = (p.n_groups + 1) >> 1;
+    const int range = item / n_gpairs;
+    const int group = (item % n_gpairs) * 2 + (int)rank;  // may be == n_groups (idle half of an odd pair)
+
+    const uint32_t *q = p.q;
+    const uint32_t *t = p.t;
+    if (p.desc != nullptr) {
+        int2 pr = reinterpret_cast<const int2 *>(p.pairs)[blockIdx.y];
+        q = p.desc + (long long)pr.x * p.frame_words;
+        t = p.desc + (long long)pr.y * p.frame_words;
+    }
+
+    const int q_first = group * (MT * kTileM);
+    // query tiles this CTA really owns (0 for the idle half) and the number of MMA chains per train tile,
+    // which is the pair's maximum: both CTAs must take part in every chain
+    const int mt_mine = max(0, min(MT, (p.nq - q_first + kTileM - 1) / kTileM));
+    const int q_first0 = (item % n_gpairs) * 2 * (MT * kTileM);
+    const int mt_pair = min(MT, (p.nq - q_first0 + kTileM - 1) / kTileM);   // leader's count >= peer's count
+    const int col_first = range * p.range_tiles * kTileN;
+    const int col_end = min(p.nt, col_first + p.range_tiles * kTileN);
+    const int n_tiles = (col_end - col_first + kTileN - 1) / kTileN;
+
+    if (tid == 0) {
+        tc::mbar_init(&bars->a_full, 2 * kExp2Threads);
+        for (int s = 0; s < kBStages2; ++s) {
+            tc::mbar_init(&bars->b_full[s], 2 * kExp2Threads);
+            tc::mbar_init(&bars->b_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&bars->acc_full[s], 1);
+            tc::mbar_init(&bars->acc_empty[s], 2 * kEpiThreads);
+        }
+        tc::fence_barrier_init();
+    }
+    const int mma_warp = kEpiWarps + kExp2Warps;
+    if (warp == mma_warp) tc::tmem_alloc_2cta(&bars->tmem_base, 512);
+    tc::tc_fence_before();
+    tc::cluster_sync();          // barrier inits + TMEM allocation visible to both CTAs
+    tc::tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp < kEpiWarps) {
+        // ===================== epilogue (own TMEM: own 128 query rows x 256 train columns) =====================
+        const int set = warp >> 2, quad = warp & 3;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        float b1[MT], b2[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { b1[m] = -FLT_MAX; b2[m] = -FLT_MAX; }
+        int job = 0;
+        for (int bt = 0; bt < n_tiles; ++bt) {
+            const int valid_cols = min(kTileN, col_end - (col_first + bt * kTileN));
+            const int n_chunks = (valid_cols + kChunk - 1) / kChunk;
+            const float chunk_bias = (float)(8191 - bt * kChunksPerTile);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                if (m < mt_pair) {
+                    const int ab = job & 1;
+                    tc::mbar_wait(&bars->acc_full[ab], (job >> 1) & 1, 10 + ab);
+                    tc::tc_fence_after();
+                    const uint32_t acc_addr = lane_addr + ab * kTileN + set * kChunk;
+                    if (m < mt_mine && n_chunks == kChunksPerTile) {
+                        uint32_t va[32], vb[32];
+                        tc::tmem_ld32_nowait(acc_addr, va);
+#pragma unroll
+                        for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
+                            uint32_t (&cur)[32] = (cc & 1) ? vb : va;
+                            uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+                            tc::tmem_ld_wait(cur);
+                            if (cc + 1 < kChunksPerTile / 2) {
+                                tc::tmem_ld32_nowait(acc_addr + (cc + 1) * 2 * kChunk, nxt);
+                            } else {
+                                tc::tc_fence_before();
+                                tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
+                            }
+                            const float key = fmaf(max32(cur), kKeyScale, chunk_bias - (float)(2 * cc + set));
+                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                            b1[m] = fmaxf(b1[m], key);
+                        }
+                    } else {
+                        if (m < mt_mine) {
+#pragma unroll
+                            for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
+                                const int c = 2 * cc + set;
+                                if (c < n_chunks) {
+                                    uint32_t v[32];
+                                    tc::tmem_ld32(acc_addr + cc * 2 * kChunk, v);
+                                    const float key = fmaf(max32(v), kKeyScale, chunk_bias - (float)c);
+                                    b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                                    b1[m] = fmaxf(b1[m], key);
+                                }
+                            }
+                        }
+                        tc::tc_fence_before();
+                        tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
+                    }
+                    ++job;
+                }
+            }
+        }
+        float2 *cand = p.cand + (long long)blockIdx.y * p.nq * p.n_ranges * 2 + (long long)range * 2 + set;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const int qi = q_first + m * kTileM + quad * 32 + lane;
+            if (m < mt_mine && qi < p.nq) cand[(long long)qi * p.n_ranges * 2] = make_float2(b1[m], b2[m]);
+        }
+    } else if (warp < mma_warp) {
+        // ===================== expanders: this CTA's query tiles + its half of every train tile =====================
+        const int et = tid - kEpiThreads;   // 0..127
+        const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
+        for (int r = et; r < mt_mine * kTileM; r += kExp2Threads) {
+            const int qi = min(q_first + r, p.nq - 1);
+            const uint4 *src = reinterpret_cast<const uint4 *>(q + (long long)qi * 8);
+            uint4 d0 = __ldg(src), d1 = __ldg(src + 1);
+            tc::expand_row_to_smem(sA_addr + (uint32_t)(r / kTileM) * kATileBytes, r % kTileM, d0, d1);
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive_cluster(&bars->a_full, 0);
+
+        auto load_row = [&](int bt, uint4 &d0, uint4 &d1) {
+            const int row = min(col_first + bt * kTileN + (int)rank * 128 + et, p.nt - 1);
+            const uint4 *src = reinterpret_cast<const uint4 *>(t + (long long)row * 8);
+            d0 = __ldg(src);
+            d1 = __ldg(src + 1);
+        };
+        uint4 n0, n1;
+        load_row(0, n0, n1);
+        int s = 0, ph = 0;
+        for (int bt = 0; bt < n_tiles; ++bt) {
+            const uint4 c0 = n0, c1 = n1;
+            if (bt + 1 < n_tiles) load_row(bt + 1, n0, n1);
+            tc::mbar_wait(&bars->b_empty[s], ph ^ 1, 20 + s);
+            tc::expand_row_to_smem(sB_addr + (uint32_t)s * kBHalfBytes, et, c0, c1);
+            tc::fence_proxy_async();
+            tc::mbar_arrive_cluster(&bars->b_full[s], 0);
+            if (++s == kBStages2) { s = 0; ph ^= 1; }
+        }
+    } else {
+        // ===================== MMA issuer: leader CTA, one elected thread =====================
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = tc::idesc_e4m3_f32(2 * kTileM, kTileN);
+            const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
+            tc::mbar_wait_cluster(&bars->a_full, 0, 30);
+            tc::tc_fence_after();
+            int job = 0, s = 0, ph = 0;
+            for (int bt = 0; bt < n_tiles; ++bt) {
+                tc::mbar_wait_cluster(&bars->b_full[s], ph, 31 + s);
+                tc::tc_fence_after();
+                for (int m = 0; m < mt_pair; ++m) {
+                    const int ab = job & 1;
+                    tc::mbar_wait_cluster(&bars->acc_empty[ab], ((job >> 1) & 1) ^ 1, 40 + ab);
+                    tc::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t ad = tc::smem_desc(sA_addr + (uint32_t)m * kATileBytes + k * 2 * tc::kLBO);
+                        const uint64_t bd = tc::smem_desc(sB_addr + (uint32_t)s * kBHalfBytes + k * 2 * tc::kLBO);
+                        tc::umma_f8_2cta(tmem + ab * kTileN, ad, bd, idesc, k > 0 ? 1u : 0u);
+                    }
+                    tc::umma_commit_2cta(&bars->acc_full[ab], 3);
+                    ++job;
+                }
+                tc::umma_commit_2cta(&bars->b_empty[s], 3);
+                if (++s == kBStages2) { s = 0; ph ^= 1; }
+            }
+        }
+        __syncwarp();
+    }
+
+    tc::tc_fence_before();
+    tc::cluster_sync();          // nobody exits while the peer may still signal its barriers / read its smem
+    if (warp == mma_warp) tc::tmem_dealloc_2cta(tmem, 512);
+}
+
 // ---- refine: exact re-scoring of the candidate chunks -------------------------------------------------
 __device__ __forceinline__ void top2_insert(unsigned long long &k1, unsigned long long &k2, unsigned long long key)
 {
@@ -271,21 +480,25 @@ __device__ __forceinline__ void top2_insert_max(unsigned long long &k1, unsigned
     k2 = max(k2, m);
 }
 
-// One warp per (problem, query).
+// G lanes per (problem, query); 32 / G queries per warp.
 //   phase 1: reduce the query's candidate chunk keys (2 per epilogue set per range) to the best two chunks of
 //            the whole train set by (max dot desc, global chunk index asc).  The exact top-2 rows lie inside
 //            them: the nearest row's chunk has the largest chunk maximum (lowest chunk on ties, because the
 //            row has the lowest index among its ties); the runner-up is either in the same chunk or is the
 //            best row outside it, which by the same argument is in the second-best chunk.
-//   phase 2: re-score those 64 rows with XOR+POPC (one row per lane and chunk) and keep the exact top-2 by
-//            (distance, global index) -- the reference tie-break.
+//   phase 2: re-score those 64 rows with XOR+POPC and keep the exact top-2 by (distance, global index) --
+//            the reference tie-break.  Keys are (distance << 6 | position), position = 0..31 in the
+//            lower-index chunk, 32..63 in the higher one, so 32-bit min == (distance, global index) order.
+template <int G>
 __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long base, unsigned long long *keys_out)
 {
-    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-    if (gw >= (long long)p.n_prob * p.nq) return;
-    const int prob = (int)(gw / p.nq);
-    const int qi = (int)(gw % p.nq);
+    constexpr int kQPW = 32 / G;   // queries per warp
+    const int lane = threadIdx.x & 31, sub = lane % G;
+    const long long gq = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kQPW + lane / G;
+    const bool live = gq < (long long)p.n_prob * p.nq;
+    const long long gqc = live ? gq : 0;
+    const int prob = (int)(gqc / p.nq);
+    const int qi = (int)(gqc % p.nq);
     const uint32_t *q = p.q;
     const uint32_t *t = p.t;
     if (p.desc != nullptr) {
@@ -293,60 +506,108 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
         q = p.desc + (long long)pr.x * p.frame_words;
         t = p.desc + (long long)pr.y * p.frame_words;
     }
-    // phase 1
+    // ---- phase 1 ----
     const int n_cand = p.n_ranges * 4;   // (range, set, slot)
-    const float *cand = reinterpret_cast<const float *>(p.cand) + gw * (long long)n_cand;
+    const float *cand = reinterpret_cast<const float *>(p.cand) + gqc * (long long)n_cand;
     const int chunks_per_range = p.range_tiles * kChunksPerTile;
     unsigned long long c1 = 0, c2 = 0;   // 0 = none; key = (dot + 257) << 32 | ~global_chunk
-    for (int ci = lane; ci < n_cand; ci += 32) {
+    auto consider = [&](int ci) {
         const float key = cand[ci];
         if (key > -1.0e30f) {
             const int ki = (int)key + 256 * 8192;
             const unsigned gchunk = (unsigned)((ci >> 2) * chunks_per_range + (8191 - (ki & 8191)));
             top2_insert_max(c1, c2, ((unsigned long long)((ki >> 13) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk));
         }
-    }
+    };
+    if (n_cand <= 8) {
+        for (int ci = 0; ci < n_cand; ++ci) consider(ci);          // every lane of the group scans all: no shuffles
+    } else {
+        for (int ci = sub; ci < n_cand; ci += G) consider(ci);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, c1, o);
-        const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, c2, o);
-        top2_insert_max(c1, c2, o1);
-        top2_insert_max(c1, c2, o2);
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, c1, o);
+            const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+            top2_insert_max(c1, c2, o1);
+            top2_insert_max(c1, c2, o2);
+        }
     }
-    // phase 2
+    // ---- phase 2 ----
+    unsigned ga = c1 ? 0xFFFFFFFFu - (unsigned)(c1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+    unsigned gb = c2 ? 0xFFFFFFFFu - (unsigned)(c2 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+    const unsigned glo = min(ga, gb), ghi = max(ga, gb);           // 0xFFFFFFFF = no such chunk
     const uint4 *qs = reinterpret_cast<const uint4 *>(q + (long long)qi * 8);
     const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
-    unsigned long long k1 = kKeyNone, k2 = kKeyNone;
+    unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-        const unsigned long long c = s == 0 ? c1 : c2;
-        if (c == 0) continue;
-        const long long row = (long long)(0xFFFFFFFFu - (unsigned)(c & 0xFFFFFFFFull)) * kChunk + lane;
-        if (row < p.nt) {
-            const uint4 *ts = reinterpret_cast<const uint4 *>(t + row * 8);
-            const uint4 ta = __ldg(ts), tb = __ldg(ts + 1);
-            const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
-                               __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
-            top2_insert(k1, k2, ((unsigned long long)d << 32) | (unsigned long long)(base + row));
+        const unsigned g = s == 0 ? glo : ghi;
+        if (g == 0xFFFFFFFFu) continue;
+#pragma unroll
+        for (int j = 0; j < 32 / G; ++j) {
+            const int pos = j * G + sub;
+            const long long row = (long long)g * kChunk + pos;
+            if (row < p.nt) {
+                const uint4 *ts = reinterpret_cast<const uint4 *>(t + row * 8);
+                const uint4 ta = __ldg(ts), tb = __ldg(ts + 1);
+                const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                                   __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+                const unsigned key = (d << 6) | (unsigned)(s * 32 + pos);
+                const unsigned m = max(k1, key);
+                k1 = min(k1, key);
+                k2 = min(k2, m);
+            }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o);
-        const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
-        top2_insert(k1, k2, o1);
-        top2_insert(k1, k2, o2);
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const unsigned o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o);
+        const unsigned o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
+        unsigned m = max(k1, o1);
+        k1 = min(k1, o1);
+        k2 = min(min(k2, o2), m);
     }
-    if (lane == 0) reinterpret_cast<ulonglong2 *>(keys_out)[gw] = make_ulonglong2(k1, k2);
+    if (live && sub == 0) {
+        auto widen = [&](unsigned k) -> unsigned long long {
+            if (k == 0xFFFFFFFFu) return kKeyNone;
+            const unsigned pos = k & 63u;
+            const long long row = (long long)(pos < 32 ? glo : ghi) * kChunk + (pos & 31u);
+            return ((unsigned long long)(k >> 6) << 32) | (unsigned long long)(base + row);
+        };
+        reinterpret_cast<ulonglong2 *>(keys_out)[gq] = make_ulonglong2(widen(k1), widen(k2));
+    }
 }
 
 template <int MT>
 int launch_tc(const TcParams &p, int n_prob, cudaStream_t stream)
 {
     const size_t smem = (size_t)MT * kATileBytes + 2 * kBTileBytes + sizeof(TcBarriers) + 64;
-    SLM_CUDA(cudaFuncSetAttribute(knn2_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool configured[64] = {};
+    int dev = 0;
+    SLM_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        SLM_CUDA(cudaFuncSetAttribute(knn2_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev & 63] = true;
+    }
     dim3 grid((unsigned)(p.n_groups * p.n_ranges), (unsigned)n_prob);
     knn2_tc_kernel<MT><<<grid, kThreads, smem, stream>>>(p);
+    SLM_CUDA(cudaGetLastError());
+    return SLM_OK;
+}
+
+template <int MT>
+int launch_tc2(const TcParams &p, int n_prob, cudaStream_t stream)
+{
+    const size_t smem = (size_t)MT * kATileBytes + kBStages2 * kBHalfBytes + sizeof(TcBarriers2) + 64;
+    static bool configured[64] = {};
+    int dev = 0;
+    SLM_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        SLM_CUDA(cudaFuncSetAttribute(knn2_tc2_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev & 63] = true;
+    }
+    const int n_gpairs = (p.n_groups + 1) / 2;
+    dim3 grid((unsigned)(2 * n_gpairs * p.n_ranges), (unsigned)n_prob);
+    knn2_tc2_kernel<MT><<<grid, kThreads2, smem, stream>>>(p);
     SLM_CUDA(cudaGetLastError());
     return SLM_OK;
 }
@@ -356,19 +617,33 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     ctx->last_variant = SLM_VARIANT_TENSOR;
     p.n_prob = n_prob;
     const int m_tiles = (p.nq + kTileM - 1) / kTileM;
-    p.mt = m_tiles >= kMaxMT ? kMaxMT : m_tiles;
-    p.n_groups = (m_tiles + p.mt - 1) / p.mt;
     const int n_tiles = (p.nt + kTileN - 1) / kTileN;
-    // ~4 work items per SM when there is enough work; ranges of at least 2 tiles, at most 1024 tiles
-    long long target = 4ll * ctx->sm_count;
-    long long n_ranges = (target + (long long)p.n_groups * n_prob - 1) / ((long long)p.n_groups * n_prob);
+    // CTA pairs (cta_group::2) need at least two query tiles to keep both halves of the M = 256 MMA busy
+    const bool two_cta = m_tiles >= 2 && !ctx->force_1cta;
+    int work_units;                      // CTAs (1-CTA kernel) or CTA pairs (2-CTA kernel) per train range
+    if (two_cta) {
+        // split the query tiles evenly over an even number of groups of at most kMaxMT2 tiles
+        int n_groups = 2 * ((m_tiles + 2 * kMaxMT2 - 1) / (2 * kMaxMT2));
+        p.mt = (m_tiles + n_groups - 1) / n_groups;
+        p.n_groups = (m_tiles + p.mt - 1) / p.mt;
+        work_units = (p.n_groups + 1) / 2;
+    } else {
+        p.mt = m_tiles >= kMaxMT ? kMaxMT : m_tiles;
+        p.n_groups = (m_tiles + p.mt - 1) / p.mt;
+        work_units = p.n_groups;
+    }
+    // Work items are sized for load balance: ~8 items per SM (or SM pair) when there is enough work, ranges of
+    // at least 2 tiles (so the one-off query expansion is amortised), at most 1024 tiles (13-bit chunk ids).
+    const long long slots = two_cta ? ctx->sm_count / 2 : ctx->sm_count;
+    long long target = 8ll * slots;
+    long long n_ranges = (target + (long long)work_units * n_prob - 1) / ((long long)work_units * n_prob);
     if (n_ranges < 1) n_ranges = 1;
     long long range_tiles = (n_tiles + n_ranges - 1) / n_ranges;
     if (range_tiles < 2) range_tiles = 2;
     if (range_tiles > kMaxRangeTiles) range_tiles = kMaxRangeTiles;
     if (range_tiles > n_tiles) range_tiles = n_tiles;
     n_ranges = (n_tiles + range_tiles - 1) / range_tiles;
-    if ((long long)p.n_groups * n_ranges > 0x7FFFFFFFll || n_prob > 65535)
+    if ((long long)p.n_groups * n_ranges > 0x3FFFFFFFll || n_prob > 65535)
         return slm_fail(SLM_ERR_UNSUPPORTED, "problem too large for one tensor-variant launch");
     p.range_tiles = (int)range_tiles;
     p.n_ranges = (int)n_ranges;
@@ -378,15 +653,29 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     p.cand = reinterpret_cast<float2 *>(ctx->scratch.p);
 
     SLM_TRY(slm_prof_begin(ctx, stream));
-    switch (p.mt) {
-    case 1: SLM_TRY(launch_tc<1>(p, n_prob, stream)); break;
-    case 2: SLM_TRY(launch_tc<2>(p, n_prob, stream)); break;
-    default: SLM_TRY(launch_tc<3>(p, n_prob, stream)); break;
+    if (two_cta) {
+        switch (p.mt) {
+        case 1: SLM_TRY(launch_tc2<1>(p, n_prob, stream)); break;
+        case 2: SLM_TRY(launch_tc2<2>(p, n_prob, stream)); break;
+        case 3: SLM_TRY(launch_tc2<3>(p, n_prob, stream)); break;
+        default: SLM_TRY(launch_tc2<4>(p, n_prob, stream)); break;
+        }
+    } else {
+        switch (p.mt) {
+        case 1: SLM_TRY(launch_tc<1>(p, n_prob, stream)); break;
+        case 2: SLM_TRY(launch_tc<2>(p, n_prob, stream)); break;
+        default: SLM_TRY(launch_tc<3>(p, n_prob, stream)); break;
+        }
     }
     SLM_TRY(slm_prof_end(ctx, stream));
-    const long long warps = (long long)n_prob * p.nq;   // one warp per (problem, query)
-    tc_refine_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p, base,
-                                                                     reinterpret_cast<unsigned long long *>(keys_out));
+    const long long n_q = (long long)n_prob * p.nq;
+    if (p.n_ranges * 4 <= 32) {       // few candidates per query (many queries, short train sets): 8 lanes each
+        tc_refine_kernel<8><<<(unsigned)((n_q + 31) / 32), 256, 0, stream>>>(
+            p, base, reinterpret_cast<unsigned long long *>(keys_out));
+    } else {                          // many ranges (long train sets): a full warp per query
+        tc_refine_kernel<32><<<(unsigned)((n_q + 7) / 8), 256, 0, stream>>>(
+            p, base, reinterpret_cast<unsigned long long *>(keys_out));
+    }
     SLM_CUDA(cudaGetLastError());
     ctx->launches += 2;
     return SLM_OK;

@@ -19,6 +19,7 @@ struct slm_ctx {
     int sm_count = 148;
     int variant = SLM_VARIANT_AUTO;
     int last_variant = 0;
+    int force_1cta = 0;   // debugging / A-B: run the single-CTA tcgen05 kernel even when CTA pairs apply
     int64_t launches = 0;
     // device buffers owned by the ctx, each grown on demand (never shrunk)
     slm_buf scratch;   // variant-internal partial results

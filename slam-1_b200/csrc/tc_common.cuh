@@ -187,4 +187,68 @@ __device__ __forceinline__ void expand_row_to_smem(uint32_t tile, int row, const
     }
 }
 
+
+// ---- 2-CTA (cta_group::2) helpers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.
+// Default semantics (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): the data handed over here
+// never travels through generic-proxy global memory -- operand tiles are published to the async proxy with
+// fence.proxy.async, accumulators with tcgen05.fence -- so no cluster/gpu-scope membar is wanted
+// (a .release.cluster arrive costs MEMBAR.ALL.GPU + ERRBAR per call: 18 % of all stall samples in the first
+// ncu capture of this kernel).
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
+{
+    asm volatile("{\n\t.reg .b32 ra;\n\t"
+                 "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+// Same, relaxed: for signals that order only tcgen05 / TMEM work (accumulator hand-back).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t *bar, uint32_t cta)
+{
+    asm volatile("{\n\t.reg .b32 ra;\n\t"
+                 "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity, int tag)
+{
+    mbar_wait(bar, parity, tag);   // local barrier; remote arrivals need no cluster-scope acquire (see above)
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t *slot_in_smem, uint32_t ncols)   // one warp in EACH CTA
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
+                 "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T with M = 256 split over the CTA pair (128 rows each); each CTA supplies
+// its own A rows and its half of the B rows from the same shared-memory offsets.  Leader CTA, one thread.
+__device__ __forceinline__ void umma_f8_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Commit to the mbarrier at this offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_2cta(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 }  // namespace tc
