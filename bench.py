@@ -110,7 +110,10 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
+
+    def reset(self):
+        self.samples, self.reasons = [], set()
 
     def start(self):
         if self.nv is not None:
@@ -268,18 +271,26 @@ def ours(args, w, cfg_id):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    # The clock sampler starts BEFORE the warm-up: its first NVML queries take milliseconds and contend with
+    # kernel submission for the driver lock, which would otherwise land inside the timed region.
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         out = step_device()
     barrier()
 
     # ---- timed region: device-resident inputs, CUDA events on the launching stream -----------------
-    sampler = ClockSampler(local)
     ctx.profile(True)
     ctx.profile_read()
     launches0 = ctx.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    sampler.start()
+    sampler.reset()
+    # one more untimed step queued directly in front of the start event: the barrier above idles the GPU for
+    # a moment and the first kernel after an idle gap runs at a lower clock.  The timed region is still
+    # exactly K steps between two events on the launching stream, with a barrier + synchronize on both sides.
+    step_device()
+    launches0 = ctx.launch_count()
     wall0 = time.perf_counter()
     if flush is None:
         evs[0][0].record()
@@ -346,7 +357,7 @@ def ours(args, w, cfg_id):
         variant = ctx.last_variant()
         per_rank_cmp = cmp_per_step / (world if sharded else 1)
         kern_avg_ms = kern_ms / max(kern_n, 1)
-        kernels_per_step = max(kern_n // max(args.steps, 1), 1)
+        kernels_per_step = max(kern_n // (args.steps + 1), 1)   # the profile also holds the ramp step
         cmp_per_launch = per_rank_cmp / kernels_per_step
         if variant == "tensor":
             # one comparison = a 256-term dot product of +-1 fp8 values = 512 flop on the tcgen05 pipe
@@ -357,16 +368,21 @@ def ours(args, w, cfg_id):
                 probe = json.load(open(os.path.join(ROOT, "profiles", "peaks_probe.json")))
             except Exception:
                 pass
-            # The kernel issues tcgen05.mma kind::f8f6f4 (2x the bf16 rate).  MEASURED_PEAKS.json only holds a
-            # cuBLAS bf16 figure, so the denominator is the HIGHER of 2 x that figure and this repo's own
-            # back-to-back tcgen05 fp8 probe on the same pool (profiles/r1_tc_probe_v1.txt).
-            peak = max(2.0 * bf16, probe.get("tcgen05_f8f6f4_tflops_burst", 0.0))
+            # The kernel issues tcgen05.mma kind::f8f6f4.  MEASURED_PEAKS.json only holds a cuBLAS bf16 figure,
+            # so the denominator is the tensor pipe's own fp8 ceiling: this repo's back-to-back tcgen05 probe
+            # measured 8191 MAC/clk/SM (profiles/r1_tc_probe_v2.txt) = the architectural 8192; times 2 flop,
+            # the SM count and the MAX SM clock (an upper bound: the kernel cannot clock higher), or 2 x the
+            # measured bf16 figure if that is larger.
+            macs = probe.get("tcgen05_f8f6f4_mac_per_clk_per_sm", 8192)
+            clk_mhz = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak = max(2.0 * bf16, macs * 2.0 * sms * clk_mhz * 1e6 / 1e12)
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": (ach / peak) if ach else None, "traffic": None,
                     "kernel": "knn2_tc_kernel", "kernel_ms": kern_avg_ms,
-                    "peak_note": ("max(2 x measured cuBLAS bf16 burst %.1f TF/s [%s], own tcgen05 kind::f8f6f4 probe %.1f TF/s)"
-                                  % (bf16, "MEASURED_PEAKS.json" if peaks else "fallback",
-                                     probe.get("tcgen05_f8f6f4_tflops_burst", 0.0))),
+                    "peak_note": ("max(2 x measured cuBLAS bf16 burst %.1f TF/s [%s], tcgen05 kind::f8f6f4 ceiling = %d MAC/clk/SM "
+                                  "(own probe) x 2 x %d SMs x %.0f MHz max SM clock)"
+                                  % (bf16, "MEASURED_PEAKS.json" if peaks else "fallback", macs, sms, clk_mhz)),
                     "frac_vs_2x_bf16_measured": (ach / (2.0 * bf16)) if ach else None,
                     "algorithmic_unit": "1 cmp = 512 fp8 flop (256-bit +-1 dot product)"}
         else:

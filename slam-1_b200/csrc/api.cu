@@ -63,22 +63,17 @@ static int pin_reserve(slm_ctx *ctx, size_t bytes)
     return SLM_OK;
 }
 
-int slm_prof_begin(slm_ctx *ctx, cudaStream_t stream)
+int slm_prof_mark(slm_ctx *ctx, cudaStream_t stream, int tag)
 {
     if (!ctx->profile || ctx->prof_n >= slm_ctx::kMaxProf) return SLM_OK;
     if (!ctx->prof_ev) {
-        ctx->prof_ev = new (std::nothrow) cudaEvent_t[2 * slm_ctx::kMaxProf];
-        if (!ctx->prof_ev) return slm_fail(SLM_ERR_NOMEM, "out of host memory");
-        for (int i = 0; i < 2 * slm_ctx::kMaxProf; ++i) SLM_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+        ctx->prof_ev = new (std::nothrow) cudaEvent_t[slm_ctx::kMaxProf];
+        ctx->prof_tag = new (std::nothrow) unsigned char[slm_ctx::kMaxProf];
+        if (!ctx->prof_ev || !ctx->prof_tag) return slm_fail(SLM_ERR_NOMEM, "out of host memory");
+        for (int i = 0; i < slm_ctx::kMaxProf; ++i) SLM_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
     }
-    SLM_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], stream));
-    return SLM_OK;
-}
-
-int slm_prof_end(slm_ctx *ctx, cudaStream_t stream)
-{
-    if (!ctx->profile || ctx->prof_n >= slm_ctx::kMaxProf || !ctx->prof_ev) return SLM_OK;
-    SLM_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], stream));
+    SLM_CUDA(cudaEventRecord(ctx->prof_ev[ctx->prof_n], stream));
+    ctx->prof_tag[ctx->prof_n] = (unsigned char)tag;
     ctx->prof_n += 1;
     return SLM_OK;
 }
@@ -160,7 +155,8 @@ int slm_create(int device, slm_ctx **ctx_out)
     if (!ctx) return slm_fail(SLM_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    ctx->force_1cta = getenv("SLM_TC_1CTA") != nullptr;   // A/B switch: single-CTA tcgen05 kernel only
+    ctx->force_1cta = getenv("SLM_TC_1CTA") != nullptr;
+    ctx->trace = getenv("SLM_TRACE") != nullptr;   // A/B switch: single-CTA tcgen05 kernel only
     SLM_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming));
@@ -178,8 +174,9 @@ int slm_destroy(slm_ctx *ctx)
         if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->prof_ev) {
-        for (int i = 0; i < 2 * slm_ctx::kMaxProf; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+        for (int i = 0; i < slm_ctx::kMaxProf; ++i) cudaEventDestroy(ctx->prof_ev[i]);
         delete[] ctx->prof_ev;
+        delete[] ctx->prof_tag;
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     for (cudaEvent_t ev : ctx->ev)
@@ -212,14 +209,24 @@ int slm_profile_read(slm_ctx *ctx, double *kernel_ms_out, int64_t *launches_out)
 {
     SLM_TRY(check_ctx(ctx));
     double total = 0.0;
-    for (int i = 0; i < ctx->prof_n; ++i) {
+    int64_t launches = 0;
+    static const char *names[] = {"call_begin", "main_begin", "main_end", "call_end"};
+    for (int i = 0; i + 1 < ctx->prof_n || i < ctx->prof_n; ++i) {
+        SLM_CUDA(cudaEventSynchronize(ctx->prof_ev[i]));
+        if (i + 1 >= ctx->prof_n) break;
         float ms = 0.f;
-        SLM_CUDA(cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
-        SLM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
-        total += ms;
+        SLM_CUDA(cudaEventSynchronize(ctx->prof_ev[i + 1]));
+        SLM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+        if (ctx->prof_tag[i] == SLM_TAG_MAIN_BEGIN && ctx->prof_tag[i + 1] == SLM_TAG_MAIN_END) {
+            total += ms;
+            launches += 1;
+        }
+        if (ctx->trace)
+            fprintf(stderr, "slm trace %4d  %-10s -> %-10s %9.3f us\n", i, names[ctx->prof_tag[i] & 3],
+                    names[ctx->prof_tag[i + 1] & 3], ms * 1e3);
     }
     if (kernel_ms_out) *kernel_ms_out = total;
-    if (launches_out) *launches_out = ctx->prof_n;
+    if (launches_out) *launches_out = launches;
     ctx->prof_n = 0;
     return SLM_OK;
 }
@@ -231,7 +238,9 @@ int slm_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t
     SLM_TRY(check_sizes(nq, nt, base));
     if (nq == 0) return SLM_OK;
     if (!q || !keys_out || (nt > 0 && !t)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
-    return knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys_out, (cudaStream_t)stream);
+    SLM_TRY(slm_prof_mark(ctx, (cudaStream_t)stream, SLM_TAG_CALL_BEGIN));
+    SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys_out, (cudaStream_t)stream));
+    return slm_prof_mark(ctx, (cudaStream_t)stream, SLM_TAG_CALL_END);
 }
 
 int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
@@ -246,6 +255,7 @@ int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)nq * 16));
     uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
+    SLM_TRY(slm_prof_mark(ctx, stream, SLM_TAG_CALL_BEGIN));
     SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys, stream));
     const uint64_t *rev = nullptr;
     if (cross_check && accept_out && nt > 0) {
@@ -254,7 +264,8 @@ int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t 
         SLM_TRY(knn2_keys_dispatch(ctx, t, nt, q, nq, 0, reinterpret_cast<uint64_t *>(ctx->rev.p), stream));
         rev = reinterpret_cast<const uint64_t *>(ctx->rev.p);
     }
-    return slm_finalize(ctx, keys, nq, ratio_num, ratio_den, rev, nt, base, idx_out, dist_out, accept_out, stream);
+    SLM_TRY(slm_finalize(ctx, keys, nq, ratio_num, ratio_den, rev, nt, base, idx_out, dist_out, accept_out, stream));
+    return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
 }
 
 int slm_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,

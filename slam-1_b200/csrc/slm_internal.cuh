@@ -35,13 +35,18 @@ struct slm_ctx {
     // optional timing of the dominant kernel (slm_profile_enable)
     int profile = 0;
     static constexpr int kMaxProf = 4096;
-    cudaEvent_t *prof_ev = nullptr;   // 2 * kMaxProf events, created lazily
+    cudaEvent_t *prof_ev = nullptr;   // kMaxProf events, created lazily
+    unsigned char *prof_tag = nullptr;
     int prof_n = 0;
+    int trace = 0;                    // SLM_TRACE=1: slm_profile_read prints every interval to stderr
 };
 
-// Bracket the dominant kernel with events when profiling is on (no-ops otherwise).
-int slm_prof_begin(slm_ctx *ctx, cudaStream_t stream);
-int slm_prof_end(slm_ctx *ctx, cudaStream_t stream);
+// Event marks on the launching stream when profiling is on (no-ops otherwise).  The dominant kernel is
+// bracketed by MAIN_BEGIN / MAIN_END; the API entry points add CALL_BEGIN / CALL_END for tracing.
+enum slm_prof_tag { SLM_TAG_CALL_BEGIN = 0, SLM_TAG_MAIN_BEGIN = 1, SLM_TAG_MAIN_END = 2, SLM_TAG_CALL_END = 3 };
+int slm_prof_mark(slm_ctx *ctx, cudaStream_t stream, int tag);
+inline int slm_prof_begin(slm_ctx *ctx, cudaStream_t stream) { return slm_prof_mark(ctx, stream, SLM_TAG_MAIN_BEGIN); }
+inline int slm_prof_end(slm_ctx *ctx, cudaStream_t stream) { return slm_prof_mark(ctx, stream, SLM_TAG_MAIN_END); }
 
 // error plumbing (api.cu)
 int slm_fail(int code, const char *fmt, ...);

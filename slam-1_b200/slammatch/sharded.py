@@ -94,7 +94,9 @@ class ShardedMatcher:
             shape = (self.world,) + tuple(keys.shape)
             if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or self._gather_buf.device != keys.device:
                 self._gather_buf = torch.empty(shape, dtype=keys.dtype, device=keys.device)
-            dist.all_gather_into_tensor(self._gather_buf, keys.contiguous(), group=self.group)
+            # output laid out as the concatenation along dim 0 (the form every backend accepts)
+            dist.all_gather_into_tensor(self._gather_buf.view((self.world * keys.shape[0],) + tuple(keys.shape[1:])),
+                                        keys.contiguous(), group=self.group)
             gathered = self._gather_buf
         else:
             gathered = keys.reshape((1,) + tuple(keys.shape))
