@@ -22,7 +22,7 @@
 // Epilogue.  Thread = one query row (one TMEM lane); it sees its row's dot products 32 columns at a time.
 // Tracking (distance, index) per element would cost more ALU than the MMA leaves room for, so the kernel
 // keeps, per row, only the best two 32-column CHUNKS by (max dot desc, chunk index asc), packed into one
-// fp32 (dot * 8192 + 8191 - chunk; exact, < 2^24) and updated with three FMNMX.  The exact top-2 rows
+// fp32 (dot * 32768 + 32767 - chunk counter; exact, < 2^24) and updated with three FMNMX.  The exact top-2 rows
 // (distance asc, index asc) of a range always lie inside its best two chunks, so a tiny second kernel
 // re-scores just those candidate rows with XOR+POPC and applies the reference tie-break bit-exactly.
 // Cost per element: ~0.5 FMNMX3; data-independent (no divergence on adversarial inputs).
@@ -44,8 +44,11 @@ constexpr int kExpThreads = kExpWarps * 32;        // 256
 constexpr int kThreads = kEpiThreads + kExpThreads + 32;   // 544
 constexpr uint32_t kATileBytes = kTileM * 256;     // 32 KB
 constexpr uint32_t kBTileBytes = kTileN * 256;     // 64 KB
-constexpr int kMaxRangeTiles = 1024;               // 8192 chunks -> 13 bits of the packed fp32 key
-constexpr float kKeyScale = 8192.0f;
+constexpr int kChunkBits = 15;                     // chunk counter bits in the packed fp32 key
+constexpr int kChunkMask = (1 << kChunkBits) - 1;  // 32767
+constexpr int kMaxEpochTiles = (1 << kChunkBits) / kChunksPerTile;   // 4096 tiles per candidate epoch
+constexpr float kKeyScale = (float)(1 << kChunkBits);
+constexpr int kKeyBias = 256 << kChunkBits;        // makes (int)key non-negative: |dot| <= 256
 
 struct TcParams {
     const uint32_t *q, *t;        // single problem
@@ -56,8 +59,11 @@ struct TcParams {
     int n_prob;
     int mt;                       // query tiles per group (1..kMaxMT)
     int n_groups;                 // ceil(nq / (128 * mt))
-    int range_tiles, n_ranges;
-    float2 *cand;                 // [n_prob][nq][n_ranges][2 sets]: best two chunk keys per epilogue set
+    int range_tiles, n_ranges;    // the train set is cut into n_ranges ranges of range_tiles 256-row tiles
+    int cpg;                      // CTAs (1-CTA kernel) / clusters (2-CTA kernel) per query group (pair):
+                                  // unit c walks ranges c, c + cpg, c + 2 cpg, ... of its group
+    int rpe, n_epochs;            // ranges per candidate epoch (rpe * range_tiles <= 4096 tiles), epochs per unit
+    float2 *cand;                 // [n_prob][nq][cpg * n_epochs][2 sets]: best two chunk keys per epilogue set
 };
 
 struct TcBarriers {
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(TcParams p)
         for (int bt = 0; bt < n_tiles; ++bt) {
             const int valid_cols = min(kTileN, col_end - (col_first + bt * kTileN));
             const int n_chunks = (valid_cols + kChunk - 1) / kChunk;
-            const float chunk_bias = (float)(8191 - bt * kChunksPerTile);
+            const float chunk_bias = (float)(kChunkMask - bt * kChunksPerTile);
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
                 if (m < mt_here) {
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(TcParams p)
                 }
             }
         }
-        // candidates of one query are contiguous: cand[prob][query][range][set] (float2 = best two chunk keys)
+        // candidates of one query are contiguous: cand[prob][query][slot = range][set] (float2 = best two chunk keys)
         float2 *cand = p.cand + (long long)blockIdx.y * p.nq * p.n_ranges * 2 + (long long)range * 2 + set;
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
@@ -283,7 +289,7 @@ struct TcBarriers2 {
 };
 
 template <int MT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_tc2_kernel(TcParams p)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(144) knn2_tc2_kernel(TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;                                   // MT tiles of 32 KB
@@ -293,9 +299,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = tc::cluster_ctarank();          // 0 = leader
     const int item = blockIdx.x >> 1;                     // cluster index
-    const int n_gpairs = (p.n_groups + 1) >> 1;
-    const int range = item / n_gpairs;
-    const int group = (item % n_gpairs) * 2 + (int)rank;  // may be == n_groups (idle half of an odd pair)
+    const int gpair = item / p.cpg;                       // pair of query groups served by this cluster
+    const int unit = item % p.cpg;                        // this cluster walks ranges unit, unit + cpg, ...
+    const int group = gpair * 2 + (int)rank;              // may be == n_groups (idle half of an odd pair)
 
     const uint32_t *q = p.q;
     const uint32_t *t = p.t;
@@ -309,11 +315,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
     // query tiles this CTA really owns (0 for the idle half) and the number of MMA chains per train tile,
     // which is the pair's maximum: both CTAs must take part in every chain
     const int mt_mine = max(0, min(MT, (p.nq - q_first + kTileM - 1) / kTileM));
-    const int q_first0 = (item % n_gpairs) * 2 * (MT * kTileM);
-    const int mt_pair = min(MT, (p.nq - q_first0 + kTileM - 1) / kTileM);   // leader's count >= peer's count
-    const int col_first = range * p.range_tiles * kTileN;
-    const int col_end = min(p.nt, col_first + p.range_tiles * kTileN);
-    const int n_tiles = (col_end - col_first + kTileN - 1) / kTileN;
+    const int mt_pair = min(MT, (p.nq - gpair * 2 * (MT * kTileM) + kTileM - 1) / kTileM);   // leader's count
+    const int total_tiles = (p.nt + kTileN - 1) / kTileN;
+    auto tiles_in_range = [&](int r) { return min(p.range_tiles, total_tiles - r * p.range_tiles); };
 
     if (tid == 0) {
         tc::mbar_init(&bars->a_full, 2 * kExp2Threads);
@@ -338,66 +342,81 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
         // ===================== epilogue (own TMEM: own 128 query rows x 256 train columns) =====================
         const int set = warp >> 2, quad = warp & 3;
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        const int n_slots = p.cpg * p.n_epochs;
+        float2 *cand = p.cand + ((long long)blockIdx.y * p.nq) * n_slots * 2 + (long long)(unit * p.n_epochs) * 2 + set;
         float b1[MT], b2[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) { b1[m] = -FLT_MAX; b2[m] = -FLT_MAX; }
-        int job = 0;
-        for (int bt = 0; bt < n_tiles; ++bt) {
-            const int valid_cols = min(kTileN, col_end - (col_first + bt * kTileN));
-            const int n_chunks = (valid_cols + kChunk - 1) / kChunk;
-            const float chunk_bias = (float)(8191 - bt * kChunksPerTile);
+        auto flush = [&](int epoch) {
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-                if (m < mt_pair) {
-                    const int ab = job & 1;
-                    tc::mbar_wait(&bars->acc_full[ab], (job >> 1) & 1, 10 + ab);
-                    tc::tc_fence_after();
-                    const uint32_t acc_addr = lane_addr + ab * kTileN + set * kChunk;
-                    if (m < mt_mine && n_chunks == kChunksPerTile) {
-                        uint32_t va[32], vb[32];
-                        tc::tmem_ld32_nowait(acc_addr, va);
+                const int qi = q_first + m * kTileM + quad * 32 + lane;
+                if (m < mt_mine && qi < p.nq) cand[(long long)qi * n_slots * 2 + epoch * 2] = make_float2(b1[m], b2[m]);
+                b1[m] = -FLT_MAX;
+                b2[m] = -FLT_MAX;
+            }
+        };
+        int job = 0, epoch = 0, lt = 0, j = 0;     // lt = tiles seen in this epoch, j = ranges walked
+        for (int r = unit; r < p.n_ranges; r += p.cpg, ++j) {
+            if (j > 0 && j % p.rpe == 0) { flush(epoch); ++epoch; lt = 0; }
+            const int col_first = r * p.range_tiles * kTileN;
+            const int col_end = min(p.nt, col_first + p.range_tiles * kTileN);
+            const int n_tiles = (col_end - col_first + kTileN - 1) / kTileN;
+            for (int bt = 0; bt < n_tiles; ++bt, ++lt) {
+                const int valid_cols = min(kTileN, col_end - (col_first + bt * kTileN));
+                const int n_chunks = (valid_cols + kChunk - 1) / kChunk;
+                const float chunk_bias = (float)(kChunkMask - lt * kChunksPerTile);
 #pragma unroll
-                        for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
-                            uint32_t (&cur)[32] = (cc & 1) ? vb : va;
-                            uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
-                            tc::tmem_ld_wait(cur);
-                            if (cc + 1 < kChunksPerTile / 2) {
-                                tc::tmem_ld32_nowait(acc_addr + (cc + 1) * 2 * kChunk, nxt);
-                            } else {
-                                tc::tc_fence_before();
-                                tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
-                            }
-                            const float key = fmaf(max32(cur), kKeyScale, chunk_bias - (float)(2 * cc + set));
-                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
-                            b1[m] = fmaxf(b1[m], key);
-                        }
-                    } else {
-                        if (m < mt_mine) {
+                for (int m = 0; m < MT; ++m) {
+                    if (m < mt_pair) {
+                        const int ab = job & 1;
+                        tc::mbar_wait(&bars->acc_full[ab], (job >> 1) & 1, 10 + ab);
+                        tc::tc_fence_after();
+                        const uint32_t acc_addr = lane_addr + ab * kTileN + set * kChunk;
+                        if (m < mt_mine && n_chunks == kChunksPerTile) {
+                            // full tile: TMEM load of chunk i+1 in flight while chunk i is reduced
+                            uint32_t va[32], vb[32];
+                            tc::tmem_ld32_nowait(acc_addr, va);
 #pragma unroll
                             for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
-                                const int c = 2 * cc + set;
-                                if (c < n_chunks) {
-                                    uint32_t v[32];
-                                    tc::tmem_ld32(acc_addr + cc * 2 * kChunk, v);
-                                    const float key = fmaf(max32(v), kKeyScale, chunk_bias - (float)c);
-                                    b2[m] = fmaxf(b2[m], fminf(b1[m], key));
-                                    b1[m] = fmaxf(b1[m], key);
+                                uint32_t (&cur)[32] = (cc & 1) ? vb : va;
+                                uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+                                tc::tmem_ld_wait(cur);
+                                if (cc + 1 < kChunksPerTile / 2) {
+                                    tc::tmem_ld32_nowait(acc_addr + (cc + 1) * 2 * kChunk, nxt);
+                                } else {
+                                    // every load of this accumulator has landed: hand it back before the last reduce
+                                    tc::tc_fence_before();
+                                    tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
+                                }
+                                const float key = fmaf(max32(cur), kKeyScale, chunk_bias - (float)(2 * cc + set));
+                                b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                                b1[m] = fmaxf(b1[m], key);
+                            }
+                        } else {
+                            if (m < mt_mine) {
+                                // last, partial tile of the train set: only chunks that contain valid columns count
+#pragma unroll
+                                for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
+                                    const int c = 2 * cc + set;
+                                    if (c < n_chunks) {
+                                        uint32_t v[32];
+                                        tc::tmem_ld32(acc_addr + cc * 2 * kChunk, v);
+                                        const float key = fmaf(max32(v), kKeyScale, chunk_bias - (float)c);
+                                        b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                                        b1[m] = fmaxf(b1[m], key);
+                                    }
                                 }
                             }
+                            tc::tc_fence_before();
+                            tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
                         }
-                        tc::tc_fence_before();
-                        tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
+                        ++job;
                     }
-                    ++job;
                 }
             }
         }
-        float2 *cand = p.cand + (long long)blockIdx.y * p.nq * p.n_ranges * 2 + (long long)range * 2 + set;
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            const int qi = q_first + m * kTileM + quad * 32 + lane;
-            if (m < mt_mine && qi < p.nq) cand[(long long)qi * p.n_ranges * 2] = make_float2(b1[m], b2[m]);
-        }
+        for (; epoch < p.n_epochs; ++epoch) flush(epoch);     // remaining epochs are written as "none"
     } else if (warp < mma_warp) {
         // ===================== expanders: this CTA's query tiles + its half of every train tile =====================
         const int et = tid - kEpiThreads;   // 0..127
@@ -411,23 +430,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
         tc::fence_proxy_async();
         tc::mbar_arrive_cluster(&bars->a_full, 0);
 
-        auto load_row = [&](int bt, uint4 &d0, uint4 &d1) {
-            const int row = min(col_first + bt * kTileN + (int)rank * 128 + et, p.nt - 1);
+        auto load_row = [&](int r, int bt, uint4 &d0, uint4 &d1) {
+            const int row = min((r * p.range_tiles + bt) * kTileN + (int)rank * 128 + et, p.nt - 1);
             const uint4 *src = reinterpret_cast<const uint4 *>(t + (long long)row * 8);
             d0 = __ldg(src);
             d1 = __ldg(src + 1);
         };
-        uint4 n0, n1;
-        load_row(0, n0, n1);
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        if (unit < p.n_ranges) load_row(unit, 0, n0, n1);
         int s = 0, ph = 0;
-        for (int bt = 0; bt < n_tiles; ++bt) {
-            const uint4 c0 = n0, c1 = n1;
-            if (bt + 1 < n_tiles) load_row(bt + 1, n0, n1);
-            tc::mbar_wait(&bars->b_empty[s], ph ^ 1, 20 + s);
-            tc::expand_row_to_smem(sB_addr + (uint32_t)s * kBHalfBytes, et, c0, c1);
-            tc::fence_proxy_async();
-            tc::mbar_arrive_cluster(&bars->b_full[s], 0);
-            if (++s == kBStages2) { s = 0; ph ^= 1; }
+        for (int r = unit; r < p.n_ranges; r += p.cpg) {
+            const int n_tiles = tiles_in_range(r);
+            for (int bt = 0; bt < n_tiles; ++bt) {
+                const uint4 c0 = n0, c1 = n1;
+                // prefetch the row of the next tile this cluster will see (possibly in its next range)
+                int r2 = r, bt2 = bt + 1;
+                if (bt2 == n_tiles) { r2 = r + p.cpg; bt2 = 0; }
+                if (r2 < p.n_ranges) load_row(r2, bt2, n0, n1);
+                tc::mbar_wait(&bars->b_empty[s], ph ^ 1, 20 + s);
+                tc::expand_row_to_smem(sB_addr + (uint32_t)s * kBHalfBytes, et, c0, c1);
+                tc::fence_proxy_async();
+                tc::mbar_arrive_cluster(&bars->b_full[s], 0);
+                if (++s == kBStages2) { s = 0; ph ^= 1; }
+            }
         }
     } else {
         // ===================== MMA issuer: leader CTA, one elected thread =====================
@@ -437,24 +462,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
             tc::mbar_wait_cluster(&bars->a_full, 0, 30);
             tc::tc_fence_after();
             int job = 0, s = 0, ph = 0;
-            for (int bt = 0; bt < n_tiles; ++bt) {
-                tc::mbar_wait_cluster(&bars->b_full[s], ph, 31 + s);
-                tc::tc_fence_after();
-                for (int m = 0; m < mt_pair; ++m) {
-                    const int ab = job & 1;
-                    tc::mbar_wait_cluster(&bars->acc_empty[ab], ((job >> 1) & 1) ^ 1, 40 + ab);
+            for (int r = unit; r < p.n_ranges; r += p.cpg) {
+                const int n_tiles = tiles_in_range(r);
+                for (int bt = 0; bt < n_tiles; ++bt) {
+                    tc::mbar_wait_cluster(&bars->b_full[s], ph, 31 + s);
                     tc::tc_fence_after();
+                    for (int m = 0; m < mt_pair; ++m) {
+                        const int ab = job & 1;
+                        tc::mbar_wait_cluster(&bars->acc_empty[ab], ((job >> 1) & 1) ^ 1, 40 + ab);
+                        tc::tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint64_t ad = tc::smem_desc(sA_addr + (uint32_t)m * kATileBytes + k * 2 * tc::kLBO);
-                        const uint64_t bd = tc::smem_desc(sB_addr + (uint32_t)s * kBHalfBytes + k * 2 * tc::kLBO);
-                        tc::umma_f8_2cta(tmem + ab * kTileN, ad, bd, idesc, k > 0 ? 1u : 0u);
+                        for (int k = 0; k < 8; ++k) {
+                            const uint64_t ad = tc::smem_desc(sA_addr + (uint32_t)m * kATileBytes + k * 2 * tc::kLBO);
+                            const uint64_t bd = tc::smem_desc(sB_addr + (uint32_t)s * kBHalfBytes + k * 2 * tc::kLBO);
+                            tc::umma_f8_2cta(tmem + ab * kTileN, ad, bd, idesc, k > 0 ? 1u : 0u);
+                        }
+                        tc::umma_commit_2cta(&bars->acc_full[ab], 3);
+                        ++job;
                     }
-                    tc::umma_commit_2cta(&bars->acc_full[ab], 3);
-                    ++job;
+                    tc::umma_commit_2cta(&bars->b_empty[s], 3);
+                    if (++s == kBStages2) { s = 0; ph ^= 1; }
                 }
-                tc::umma_commit_2cta(&bars->b_empty[s], 3);
-                if (++s == kBStages2) { s = 0; ph ^= 1; }
             }
         }
         __syncwarp();
@@ -507,16 +535,20 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
         t = p.desc + (long long)pr.y * p.frame_words;
     }
     // ---- phase 1 ----
-    const int n_cand = p.n_ranges * 4;   // (range, set, slot)
+    const int n_cand = p.cpg * p.n_epochs * 4;   // (unit, epoch, set, best/second)
     const float *cand = reinterpret_cast<const float *>(p.cand) + gqc * (long long)n_cand;
-    const int chunks_per_range = p.range_tiles * kChunksPerTile;
     unsigned long long c1 = 0, c2 = 0;   // 0 = none; key = (dot + 257) << 32 | ~global_chunk
     auto consider = [&](int ci) {
         const float key = cand[ci];
         if (key > -1.0e30f) {
-            const int ki = (int)key + 256 * 8192;
-            const unsigned gchunk = (unsigned)((ci >> 2) * chunks_per_range + (8191 - (ki & 8191)));
-            top2_insert_max(c1, c2, ((unsigned long long)((ki >> 13) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk));
+            // key = dot * 2^15 + (32767 - chunk counter of the unit's epoch); undo the unit's strided range walk
+            const int ki = (int)key + kKeyBias;
+            const int lc = kChunkMask - (ki & kChunkMask);
+            const int slot = ci >> 2, unit = slot / p.n_epochs, epoch = slot % p.n_epochs;
+            const int lt = lc >> 3;                                   // tile counter inside the epoch
+            const int range = unit + (epoch * p.rpe + lt / p.range_tiles) * p.cpg;
+            const unsigned gchunk = (unsigned)((range * p.range_tiles + lt % p.range_tiles) * kChunksPerTile + (lc & 7));
+            top2_insert_max(c1, c2, ((unsigned long long)((ki >> kChunkBits) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk));
         }
     };
     if (n_cand <= 8) {
@@ -606,7 +638,7 @@ int launch_tc2(const TcParams &p, int n_prob, cudaStream_t stream)
         configured[dev & 63] = true;
     }
     const int n_gpairs = (p.n_groups + 1) / 2;
-    dim3 grid((unsigned)(2 * n_gpairs * p.n_ranges), (unsigned)n_prob);
+    dim3 grid((unsigned)(2 * n_gpairs * p.cpg), (unsigned)n_prob);
     knn2_tc2_kernel<MT><<<grid, kThreads2, smem, stream>>>(p);
     SLM_CUDA(cudaGetLastError());
     return SLM_OK;
@@ -632,23 +664,48 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         p.n_groups = (m_tiles + p.mt - 1) / p.mt;
         work_units = p.n_groups;
     }
-    // Work items are sized for load balance: ~8 items per SM (or SM pair) when there is enough work, ranges of
-    // at least 2 tiles (so the one-off query expansion is amortised), at most 1024 tiles (13-bit chunk ids).
-    const long long slots = two_cta ? ctx->sm_count / 2 : ctx->sm_count;
-    long long target = 8ll * slots;
-    long long n_ranges = (target + (long long)work_units * n_prob - 1) / ((long long)work_units * n_prob);
-    if (n_ranges < 1) n_ranges = 1;
-    long long range_tiles = (n_tiles + n_ranges - 1) / n_ranges;
-    if (range_tiles < 2) range_tiles = 2;
-    if (range_tiles > kMaxRangeTiles) range_tiles = kMaxRangeTiles;
-    if (range_tiles > n_tiles) range_tiles = n_tiles;
-    n_ranges = (n_tiles + range_tiles - 1) / range_tiles;
-    if ((long long)p.n_groups * n_ranges > 0x3FFFFFFFll || n_prob > 65535)
-        return slm_fail(SLM_ERR_UNSUPPORTED, "problem too large for one tensor-variant launch");
-    p.range_tiles = (int)range_tiles;
-    p.n_ranges = (int)n_ranges;
+    if (two_cta) {
+        // CTA pairs.  `units` = (group pair, problem) combinations; each gets `cpg` clusters that walk the train
+        // ranges with stride cpg.  Few units (long train sets): one resident wave, the query tiles are expanded
+        // once per cluster and short ranges keep the static stride balanced.  Many units: ~16 waves of clusters.
+        const long long slots = ctx->sm_count / 2;
+        const long long units = (long long)work_units * n_prob;
+        long long cpg = units * 2 <= slots ? slots / units : (16 * slots + units - 1) / units;
+        if (cpg > n_tiles) cpg = n_tiles;
+        if (cpg < 1) cpg = 1;
+        long long range_tiles = n_tiles / (cpg * 32);
+        if (range_tiles < 1) range_tiles = 1;
+        if (range_tiles > 8) range_tiles = 8;
+        const long long n_ranges = (n_tiles + range_tiles - 1) / range_tiles;
+        const long long rpe = kMaxEpochTiles / range_tiles;
+        const long long ranges_per_unit = (n_ranges + cpg - 1) / cpg;
+        p.cpg = (int)cpg;
+        p.range_tiles = (int)range_tiles;
+        p.n_ranges = (int)n_ranges;
+        p.rpe = (int)rpe;
+        p.n_epochs = (int)((ranges_per_unit + rpe - 1) / rpe);
+        if (units * cpg > 0x3FFFFFFFll) return slm_fail(SLM_ERR_UNSUPPORTED, "problem too large for one launch");
+    } else {
+        // single CTAs (fewer than two query tiles): one contiguous range per CTA, ~8 CTAs per SM when possible
+        const long long slots = ctx->sm_count;
+        long long n_ranges = (8 * slots + (long long)work_units * n_prob - 1) / ((long long)work_units * n_prob);
+        if (n_ranges < 1) n_ranges = 1;
+        long long range_tiles = (n_tiles + n_ranges - 1) / n_ranges;
+        if (range_tiles < 2) range_tiles = 2;
+        if (range_tiles > kMaxEpochTiles) range_tiles = kMaxEpochTiles;
+        if (range_tiles > n_tiles) range_tiles = n_tiles;
+        n_ranges = (n_tiles + range_tiles - 1) / range_tiles;
+        if ((long long)p.n_groups * n_ranges > 0x3FFFFFFFll)
+            return slm_fail(SLM_ERR_UNSUPPORTED, "problem too large for one launch");
+        p.range_tiles = (int)range_tiles;
+        p.n_ranges = (int)n_ranges;
+        p.cpg = (int)n_ranges;
+        p.rpe = 1;
+        p.n_epochs = 1;
+    }
+    if (n_prob > 65535) return slm_fail(SLM_ERR_UNSUPPORTED, "at most 65535 problems per launch");
 
-    const size_t cand_bytes = (size_t)n_prob * (size_t)n_ranges * 2 * (size_t)p.nq * sizeof(float2);
+    const size_t cand_bytes = (size_t)n_prob * (size_t)p.cpg * p.n_epochs * 2 * (size_t)p.nq * sizeof(float2);
     SLM_TRY(slm_buf_reserve(ctx, &ctx->scratch, cand_bytes));
     p.cand = reinterpret_cast<float2 *>(ctx->scratch.p);
 
@@ -669,7 +726,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     }
     SLM_TRY(slm_prof_end(ctx, stream));
     const long long n_q = (long long)n_prob * p.nq;
-    if (p.n_ranges * 4 <= 32) {       // few candidates per query (many queries, short train sets): 8 lanes each
+    if (p.cpg * p.n_epochs * 4 <= 32) {   // few candidates per query (many queries, short train sets): 8 lanes each
         tc_refine_kernel<8><<<(unsigned)((n_q + 31) / 32), 256, 0, stream>>>(
             p, base, reinterpret_cast<unsigned long long *>(keys_out));
     } else {                          // many ranges (long train sets): a full warp per query
