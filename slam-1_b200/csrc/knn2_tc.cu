@@ -274,9 +274,11 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(TcParams p)
 // Barriers: "full" barriers live in the leader and collect arrivals from both CTAs (remote arrives);
 // "empty"/"acc_full" barriers are signalled into both CTAs by multicast tcgen05.commit.
 // =====================================================================================================
-constexpr int kExp2Warps = 4;
-constexpr int kExp2Threads = kExp2Warps * 32;                 // 128 = rows of a B half tile
-constexpr int kThreads2 = kEpiThreads + kExp2Threads + 32;    // 416
+// 12 warps = 384 threads: register allocation is per 4 warps, so a 13th warp would cap the kernel at 128
+// registers per thread; the 128 rows of a half tile are therefore spread over 3 expander warps.
+constexpr int kExp2Warps = 3;
+constexpr int kExp2Threads = kExp2Warps * 32;                 // 96
+constexpr int kThreads2 = kEpiThreads + kExp2Threads + 32;    // 384
 constexpr uint32_t kBHalfBytes = 128 * 256;                   // 32 KB
 constexpr int kBStages2 = 3;
 constexpr int kMaxMT2 = 4;
@@ -289,7 +291,7 @@ struct TcBarriers2 {
 };
 
 template <int MT>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(144) knn2_tc2_kernel(TcParams p)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_tc2_kernel(TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;                                   // MT tiles of 32 KB
@@ -430,25 +432,34 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(144) knn2_tc2_kernel(TcPar
         tc::fence_proxy_async();
         tc::mbar_arrive_cluster(&bars->a_full, 0);
 
-        auto load_row = [&](int r, int bt, uint4 &d0, uint4 &d1) {
-            const int row = min((r * p.range_tiles + bt) * kTileN + (int)rank * 128 + et, p.nt - 1);
+        // 128 rows per half tile over 96 threads: thread et expands row et, threads 0..31 also row 96 + et
+        const bool two_rows = et < 128 - kExp2Threads;
+        auto load_row = [&](int r, int bt, int row_in_half, uint4 &d0, uint4 &d1) {
+            const int row = min((r * p.range_tiles + bt) * kTileN + (int)rank * 128 + row_in_half, p.nt - 1);
             const uint4 *src = reinterpret_cast<const uint4 *>(t + (long long)row * 8);
             d0 = __ldg(src);
             d1 = __ldg(src + 1);
         };
-        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-        if (unit < p.n_ranges) load_row(unit, 0, n0, n1);
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, m0 = n0, m1 = n0;
+        if (unit < p.n_ranges) {
+            load_row(unit, 0, et, n0, n1);
+            if (two_rows) load_row(unit, 0, et + kExp2Threads, m0, m1);
+        }
         int s = 0, ph = 0;
         for (int r = unit; r < p.n_ranges; r += p.cpg) {
             const int n_tiles = tiles_in_range(r);
             for (int bt = 0; bt < n_tiles; ++bt) {
-                const uint4 c0 = n0, c1 = n1;
-                // prefetch the row of the next tile this cluster will see (possibly in its next range)
+                const uint4 c0 = n0, c1 = n1, e0 = m0, e1 = m1;
+                // prefetch the rows of the next tile this cluster will see (possibly in its next range)
                 int r2 = r, bt2 = bt + 1;
                 if (bt2 == n_tiles) { r2 = r + p.cpg; bt2 = 0; }
-                if (r2 < p.n_ranges) load_row(r2, bt2, n0, n1);
+                if (r2 < p.n_ranges) {
+                    load_row(r2, bt2, et, n0, n1);
+                    if (two_rows) load_row(r2, bt2, et + kExp2Threads, m0, m1);
+                }
                 tc::mbar_wait(&bars->b_empty[s], ph ^ 1, 20 + s);
                 tc::expand_row_to_smem(sB_addr + (uint32_t)s * kBHalfBytes, et, c0, c1);
+                if (two_rows) tc::expand_row_to_smem(sB_addr + (uint32_t)s * kBHalfBytes, et + kExp2Threads, e0, e1);
                 tc::fence_proxy_async();
                 tc::mbar_arrive_cluster(&bars->b_full[s], 0);
                 if (++s == kBStages2) { s = 0; ph ^= 1; }
