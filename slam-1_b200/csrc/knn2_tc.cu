@@ -227,10 +227,10 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(TcParams p)
             tc::mbar_arrive(&bars->b_full[s]);
         }
     } else {
-        // ===================== MMA issuer: one elected thread =====================
-        if (lane == 0) {
+        // ===================== MMA issuer: the warp stays converged, one elected lane issues =====================
+        {
             const uint32_t idesc = tc::idesc_e4m3_f32(kTileM, kTileN);
-            const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
+            const uint32_t a_lo0 = tc::smem_desc_lo(tc::smem_u32(sA)), b_lo0 = tc::smem_desc_lo(tc::smem_u32(sB));
             tc::mbar_wait(&bars->a_full, 0, 30);
             tc::tc_fence_after();
             int job = 0;
@@ -242,19 +242,17 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(TcParams p)
                     const int ab = job & 1;
                     tc::mbar_wait(&bars->acc_empty[ab], ((job >> 1) & 1) ^ 1, 33 + ab);
                     tc::tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint64_t ad = tc::smem_desc(sA_addr + (uint32_t)m * kATileBytes + k * 2 * tc::kLBO);
-                        const uint64_t bd = tc::smem_desc(sB_addr + (uint32_t)s * kBTileBytes + k * 2 * tc::kLBO);
-                        tc::umma_f8(tmem + ab * kTileN, ad, bd, idesc, k > 0 ? 1u : 0u);
+                    if (tc::elect_one()) {
+                        tc::umma_job<1>(tmem + ab * kTileN, a_lo0 + m * (kATileBytes >> 4), b_lo0 + s * (kBTileBytes >> 4), idesc);
+                        tc::umma_commit(&bars->acc_full[ab]);
                     }
-                    tc::umma_commit(&bars->acc_full[ab]);
+                    __syncwarp();
                     ++job;
                 }
-                tc::umma_commit(&bars->b_empty[s]);
+                if (tc::elect_one()) tc::umma_commit(&bars->b_empty[s]);
+                __syncwarp();
             }
         }
-        __syncwarp();
     }
 
     tc::tc_fence_before();
@@ -466,10 +464,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
             }
         }
     } else {
-        // ===================== MMA issuer: leader CTA, one elected thread =====================
-        if (rank == 0 && lane == 0) {
+        // ===================== MMA issuer: leader CTA; the warp stays converged, one elected lane issues ==========
+        if (rank == 0) {
             const uint32_t idesc = tc::idesc_e4m3_f32(2 * kTileM, kTileN);
-            const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
+            const uint32_t a_lo0 = tc::smem_desc_lo(tc::smem_u32(sA)), b_lo0 = tc::smem_desc_lo(tc::smem_u32(sB));
             tc::mbar_wait_cluster(&bars->a_full, 0, 30);
             tc::tc_fence_after();
             int job = 0, s = 0, ph = 0;
@@ -478,25 +476,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
                 for (int bt = 0; bt < n_tiles; ++bt) {
                     tc::mbar_wait_cluster(&bars->b_full[s], ph, 31 + s);
                     tc::tc_fence_after();
+                    const uint32_t b_lo = b_lo0 + s * (kBHalfBytes >> 4);
                     for (int m = 0; m < mt_pair; ++m) {
                         const int ab = job & 1;
                         tc::mbar_wait_cluster(&bars->acc_empty[ab], ((job >> 1) & 1) ^ 1, 40 + ab);
                         tc::tc_fence_after();
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const uint64_t ad = tc::smem_desc(sA_addr + (uint32_t)m * kATileBytes + k * 2 * tc::kLBO);
-                            const uint64_t bd = tc::smem_desc(sB_addr + (uint32_t)s * kBHalfBytes + k * 2 * tc::kLBO);
-                            tc::umma_f8_2cta(tmem + ab * kTileN, ad, bd, idesc, k > 0 ? 1u : 0u);
+                        if (tc::elect_one()) {
+                            tc::umma_job<2>(tmem + ab * kTileN, a_lo0 + m * (kATileBytes >> 4), b_lo, idesc);
+                            tc::umma_commit_2cta(&bars->acc_full[ab], 3);
                         }
-                        tc::umma_commit_2cta(&bars->acc_full[ab], 3);
+                        __syncwarp();
                         ++job;
                     }
-                    tc::umma_commit_2cta(&bars->b_empty[s], 3);
+                    if (tc::elect_one()) tc::umma_commit_2cta(&bars->b_empty[s], 3);
+                    __syncwarp();
                     if (++s == kBStages2) { s = 0; ph ^= 1; }
                 }
             }
         }
-        __syncwarp();
     }
 
     tc::tc_fence_before();
