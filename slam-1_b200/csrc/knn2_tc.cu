@@ -374,25 +374,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
                         tc::tc_fence_after();
                         const uint32_t acc_addr = lane_addr + ab * kTileN + set * kChunk;
                         if (m < mt_mine && n_chunks == kChunksPerTile) {
-                            // full tile: TMEM load of chunk i+1 in flight while chunk i is reduced
-                            uint32_t va[32], vb[32];
-                            tc::tmem_ld32_nowait(acc_addr, va);
-#pragma unroll
-                            for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
-                                uint32_t (&cur)[32] = (cc & 1) ? vb : va;
-                                uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
-                                tc::tmem_ld_wait(cur);
-                                if (cc + 1 < kChunksPerTile / 2) {
-                                    tc::tmem_ld32_nowait(acc_addr + (cc + 1) * 2 * kChunk, nxt);
-                                } else {
-                                    // every load of this accumulator has landed: hand it back before the last reduce
-                                    tc::tc_fence_before();
-                                    tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
-                                }
-                                const float key = fmaf(max32(cur), kKeyScale, chunk_bias - (float)(2 * cc + set));
-                                b2[m] = fmaxf(b2[m], fminf(b1[m], key));
-                                b1[m] = fmaxf(b1[m], key);
-                            }
+                            // full tile: all four TMEM loads of this warp in flight at once; the accumulator is
+                            // handed back as soon as they have landed, BEFORE the reduction -- with two accumulators
+                            // the MMA may only run ahead by one job, so the hand-back latency is on the critical path
+                            uint32_t v0[32], v1[32], v2[32], v3[32];
+                            tc::tmem_ld32_nowait(acc_addr + 0 * kChunk, v0);
+                            tc::tmem_ld32_nowait(acc_addr + 2 * kChunk, v1);
+                            tc::tmem_ld32_nowait(acc_addr + 4 * kChunk, v2);
+                            tc::tmem_ld32_nowait(acc_addr + 6 * kChunk, v3);
+                            tc::tmem_ld_wait(v0);
+                            tc::pin_regs(v1);
+                            tc::pin_regs(v2);
+                            tc::pin_regs(v3);
+                            tc::tc_fence_before();
+                            tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
+                            const float base_bias = chunk_bias - (float)set;
+                            float key = fmaf(max32(v0), kKeyScale, base_bias);
+                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                            b1[m] = fmaxf(b1[m], key);
+                            key = fmaf(max32(v1), kKeyScale, base_bias - 2.0f);
+                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                            b1[m] = fmaxf(b1[m], key);
+                            key = fmaf(max32(v2), kKeyScale, base_bias - 4.0f);
+                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                            b1[m] = fmaxf(b1[m], key);
+                            key = fmaf(max32(v3), kKeyScale, base_bias - 6.0f);
+                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
+                            b1[m] = fmaxf(b1[m], key);
                         } else {
                             if (m < mt_mine) {
                                 // last, partial tile of the train set: only chunks that contain valid columns count

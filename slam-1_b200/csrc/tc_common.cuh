@@ -148,6 +148,18 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32])
                  :: "memory");
 }
 
+// Pins the consumers of v behind this point in program order without emitting an instruction (used after a
+// single tcgen05.wait::ld that covers several outstanding loads).
+__device__ __forceinline__ void pin_regs(uint32_t (&v)[32])
+{
+    asm volatile(""
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
+
 // ---- bit -> fp8 (+-1) expansion -----------------------------------------------------------------------
 // The contraction index K may be permuted freely as long as both operands use the same permutation, so
 // the expansion picks the cheapest bit -> byte mapping: output word k of a 32-bit descriptor word w is
