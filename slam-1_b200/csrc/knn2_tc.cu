@@ -686,9 +686,18 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         // once per cluster and short ranges keep the static stride balanced.  Many units: ~16 waves of clusters.
         const long long slots = ctx->sm_count / 2;
         const long long units = (long long)work_units * n_prob;
-        long long cpg = units * 2 <= slots ? slots / units : (16 * slots + units - 1) / units;
-        if (cpg > n_tiles) cpg = n_tiles;
-        if (cpg < 1) cpg = 1;
+        // Clusters per unit: minimise  waves x (start-up + tiles per cluster x cycles per tile)  with
+        // waves = ceil(units * cpg / cluster slots).  Few units (long train sets) end up as one resident wave,
+        // many units as several waves of longer-lived clusters.
+        const double kStartupClk = 6000.0, kTileClk = 1024.0 * p.mt;
+        long long cpg = 1;
+        double best = 1e300;
+        const long long cpg_max = n_tiles < 4 * slots ? n_tiles : 4 * slots;
+        for (long long c = 1; c <= cpg_max; ++c) {
+            const long long waves = (units * c + slots - 1) / slots;
+            const double cost = (double)waves * (kStartupClk + (double)((n_tiles + c - 1) / c) * kTileClk);
+            if (cost < best * 0.999) { best = cost; cpg = c; }
+        }
         long long range_tiles = n_tiles / (cpg * 32);
         if (range_tiles < 1) range_tiles = 1;
         if (range_tiles > 8) range_tiles = 8;
