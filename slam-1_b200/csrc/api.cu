@@ -179,6 +179,9 @@ int slm_destroy(slm_ctx *ctx)
         delete[] ctx->prof_tag;
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (cudaEvent_t ev : ctx->chunk_ev)
+        if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     delete ctx;
@@ -313,11 +316,8 @@ int slm_merge_top2(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int
     if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
     if (nq == 0) return SLM_OK;
     if (!gathered) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
-    cudaStream_t stream = (cudaStream_t)stream_;
-    SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)nq * 16));
-    uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
-    SLM_TRY(slm_merge_keys(ctx, gathered, n_shards, nq, keys, stream));
-    return slm_finalize(ctx, keys, nq, ratio_num, ratio_den, nullptr, 0, 0, idx_out, dist_out, accept_out, stream);
+    return slm_merge_finalize(ctx, gathered, n_shards, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out,
+                              (cudaStream_t)stream_);
 }
 
 int slm_compact_matches(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
@@ -356,9 +356,32 @@ int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t
     SLM_CUDA(cudaEventSynchronize(ctx->ev[0]));  // a batched call may still be reading the pinned block
 
     SLM_CUDA(cudaMemcpyAsync(q_dev, q_host, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
-    if (nt > 0) SLM_CUDA(cudaMemcpyAsync(t_dev, t_host, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
-    SLM_TRY(slm_knn2_filter(ctx, q_dev, nq, t_dev, nt, 0, ratio_num, ratio_den, cross_check, idx_dev, dist_dev,
-                            accept_out ? acc_dev : nullptr, s));
+    // Large train sets: the H2D copy (PCIe) takes longer than the search, so it is cut into chunks on a second
+    // stream and every chunk is searched as soon as it has landed -- chunk = shard: per-chunk packed top-2 keys
+    // are merged by global index exactly like the cross-GPU path.  (Cross-check needs the whole train set
+    // resident for the reverse search, so it takes the plain path.)
+    const int64_t kChunkRows = 1 << 20;          // 32 MB
+    const int64_t n_chunks = (nt + kChunkRows - 1) / kChunkRows;
+    if (n_chunks >= 3 && n_chunks <= kMaxHostChunks && !cross_check) {
+        SLM_TRY(slm_buf_reserve(ctx, &ctx->rev, (size_t)n_chunks * nq * 16));
+        uint64_t *chunk_keys = reinterpret_cast<uint64_t *>(ctx->rev.p);
+        if (!ctx->copy_stream) SLM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int64_t c = 0; c < n_chunks; ++c) {
+            const int64_t r0 = c * kChunkRows, rows = (nt - r0 < kChunkRows) ? nt - r0 : kChunkRows;
+            if (!ctx->chunk_ev[c]) SLM_CUDA(cudaEventCreateWithFlags(&ctx->chunk_ev[c], cudaEventDisableTiming));
+            SLM_CUDA(cudaMemcpyAsync(t_dev + r0 * 8, t_host + r0 * 32, (size_t)rows * 32, cudaMemcpyHostToDevice,
+                                     ctx->copy_stream));
+            SLM_CUDA(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+            SLM_CUDA(cudaStreamWaitEvent(s, ctx->chunk_ev[c], 0));
+            SLM_TRY(knn2_keys_dispatch(ctx, q_dev, nq, t_dev + r0 * 8, rows, r0, chunk_keys + c * nq * 2, s));
+        }
+        SLM_TRY(slm_merge_finalize(ctx, chunk_keys, (int32_t)n_chunks, nq, ratio_num, ratio_den, idx_dev, dist_dev,
+                                   accept_out ? acc_dev : nullptr, s));
+    } else {
+        if (nt > 0) SLM_CUDA(cudaMemcpyAsync(t_dev, t_host, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+        SLM_TRY(slm_knn2_filter(ctx, q_dev, nq, t_dev, nt, 0, ratio_num, ratio_den, cross_check, idx_dev, dist_dev,
+                                accept_out ? acc_dev : nullptr, s));
+    }
     if (idx_out) SLM_CUDA(cudaMemcpyAsync(pin, idx_dev, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
     if (dist_out) SLM_CUDA(cudaMemcpyAsync(pin + i_b, dist_dev, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
     if (accept_out) SLM_CUDA(cudaMemcpyAsync(pin + 2 * i_b, acc_dev, (size_t)nq, cudaMemcpyDeviceToHost, s));

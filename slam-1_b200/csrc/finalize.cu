@@ -48,6 +48,31 @@ __global__ void merge_keys_kernel(const unsigned long long *gathered, int n_shar
     reinterpret_cast<ulonglong2 *>(keys_out)[i] = make_ulonglong2(k1, k2);
 }
 
+// Cross-shard merge fused with the finalize step (one launch on the latency-critical sharded path).
+__global__ void merge_finalize_kernel(const unsigned long long *gathered, int n_shards, long long nq, int ratio_num,
+                                      int ratio_den, int *idx_out, int *dist_out, unsigned char *accept_out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    unsigned long long k1 = kKeyNone, k2 = kKeyNone;
+    for (int s = 0; s < n_shards; ++s) {
+        ulonglong2 v = reinterpret_cast<const ulonglong2 *>(gathered)[(long long)s * nq + i];
+        unsigned long long m = max(k1, v.x);
+        k1 = min(k1, v.x);
+        k2 = min(k2, m);
+        m = max(k1, v.y);
+        k1 = min(k1, v.y);
+        k2 = min(k2, m);
+    }
+    const bool has1 = k1 != kKeyNone, has2 = k2 != kKeyNone;
+    const int i1 = has1 ? (int)(k1 & 0xFFFFFFFFull) : -1, d1 = has1 ? (int)(k1 >> 32) : -1;
+    const int i2 = has2 ? (int)(k2 & 0xFFFFFFFFull) : -1, d2 = has2 ? (int)(k2 >> 32) : -1;
+    if (idx_out) reinterpret_cast<int2 *>(idx_out)[i] = make_int2(i1, i2);
+    if (dist_out) reinterpret_cast<int2 *>(dist_out)[i] = make_int2(d1, d2);
+    if (accept_out)
+        accept_out[i] = (ratio_num > 0 ? (has1 && has2 && (long long)ratio_den * d1 < (long long)ratio_num * d2) : has1) ? 1 : 0;
+}
+
 // Ordered compaction by one CTA: block-wide exclusive scan over 1024-row chunks.
 constexpr int kCompactThreads = 1024;
 __global__ void __launch_bounds__(kCompactThreads)
@@ -125,6 +150,18 @@ int slm_merge_keys(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int
     merge_keys_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(
         reinterpret_cast<const unsigned long long *>(gathered), n_shards, nq,
         reinterpret_cast<unsigned long long *>(keys_out));
+    SLM_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SLM_OK;
+}
+
+int slm_merge_finalize(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int64_t nq, int32_t ratio_num,
+                       int32_t ratio_den, int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream)
+{
+    if (nq <= 0) return SLM_OK;
+    merge_finalize_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const unsigned long long *>(gathered), n_shards, nq, ratio_num, ratio_den, idx_out, dist_out,
+        accept_out);
     SLM_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return SLM_OK;

@@ -698,7 +698,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
             const double cost = (double)waves * (kStartupClk + (double)((n_tiles + c - 1) / c) * kTileClk);
             if (cost < best * 0.999) { best = cost; cpg = c; }
         }
-        long long range_tiles = n_tiles / (cpg * 32);
+        long long range_tiles = n_tiles / (cpg * 128);      // short ranges: the static stride stays balanced
         if (range_tiles < 1) range_tiles = 1;
         if (range_tiles > 8) range_tiles = 8;
         const long long n_ranges = (n_tiles + range_tiles - 1) / range_tiles;

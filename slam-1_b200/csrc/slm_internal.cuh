@@ -9,6 +9,8 @@
 // Unsigned order of the key == OpenCV's (distance, trainIdx) order.
 static constexpr unsigned long long kKeyNone = 0xFFFFFFFFFFFFFFFFull;
 
+static constexpr int kMaxHostChunks = 256;   // x 1M rows per chunk
+
 struct slm_buf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -31,6 +33,8 @@ struct slm_ctx {
     void *pin = nullptr;
     size_t pin_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;           // H2D chunks of slm_knn2_host
+    cudaEvent_t chunk_ev[kMaxHostChunks] = {};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // optional timing of the dominant kernel (slm_profile_enable)
     int profile = 0;
@@ -93,6 +97,8 @@ int slm_finalize(slm_ctx *ctx, const uint64_t *keys, int64_t n, int32_t ratio_nu
                  int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
 int slm_merge_keys(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int64_t nq,
                    uint64_t *keys_out, cudaStream_t stream);
+int slm_merge_finalize(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int64_t nq, int32_t ratio_num,
+                       int32_t ratio_den, int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
 int slm_compact(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
                 int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, cudaStream_t stream);
 

@@ -48,7 +48,7 @@ class ShardedMatcher:
         self._local_keys = local_keys or self._cuda_local_keys
         self._merge = merge or self._cuda_merge
         self._variant = variant
-        self._gather_buf = None
+        self._gather_bufs = {}
 
     # -- CUDA implementations ---------------------------------------------------------------------
     def _ctx(self):
@@ -85,19 +85,40 @@ class ShardedMatcher:
         return idx, dist_, acc
 
     # -- the sharded query ----------------------------------------------------------------------------
-    def knn2(self, q):
-        """Local top-2 keys -> all-gather -> merge.  Every rank returns the full, identical result."""
+    def _gather(self, keys, slot, async_op=False):
         import torch
         import torch.distributed as dist
-        keys = self._local_keys(q)
-        if self.world > 1:
-            shape = (self.world,) + tuple(keys.shape)
-            if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or self._gather_buf.device != keys.device:
-                self._gather_buf = torch.empty(shape, dtype=keys.dtype, device=keys.device)
-            # output laid out as the concatenation along dim 0 (the form every backend accepts)
-            dist.all_gather_into_tensor(self._gather_buf.view((self.world * keys.shape[0],) + tuple(keys.shape[1:])),
-                                        keys.contiguous(), group=self.group)
-            gathered = self._gather_buf
-        else:
-            gathered = keys.reshape((1,) + tuple(keys.shape))
-        return self._merge(gathered)
+        shape = (self.world,) + tuple(keys.shape)
+        buf = self._gather_bufs.get(slot)
+        if buf is None or tuple(buf.shape) != shape or buf.device != keys.device:
+            buf = torch.empty(shape, dtype=keys.dtype, device=keys.device)
+            self._gather_bufs[slot] = buf
+        # output laid out as the concatenation along dim 0 (the form every backend accepts)
+        work = dist.all_gather_into_tensor(buf.view((self.world * keys.shape[0],) + tuple(keys.shape[1:])),
+                                           keys.contiguous(), group=self.group, async_op=async_op)
+        return buf, work
+
+    def knn2(self, q, query_batch: int = 1 << 18):
+        """Local top-2 keys -> all-gather -> merge.  Every rank returns the full, identical result.
+
+        Large query sets (config 4: 1M descriptors) are cut into batches so that the all-gather of batch b
+        (16 bytes per query and rank) overlaps the search of batch b+1; small ones take one pass."""
+        import torch
+        keys_fn, nq = self._local_keys, q.shape[0]
+        if self.world == 1:
+            keys = keys_fn(q)
+            return self._merge(keys.reshape((1,) + tuple(keys.shape)))
+        if nq <= query_batch:
+            buf, _ = self._gather(keys_fn(q), 0)
+            return self._merge(buf)
+        outs, pending = [], None
+        for b, s in enumerate(range(0, nq, query_batch)):
+            keys = keys_fn(q[s:s + query_batch])
+            buf, work = self._gather(keys, b & 1, async_op=True)
+            if pending is not None:
+                pending[1].wait()
+                outs.append(self._merge(pending[0]))
+            pending = (buf, work, keys)          # keep `keys` alive until its gather has been consumed
+        pending[1].wait()
+        outs.append(self._merge(pending[0]))
+        return tuple(torch.cat([o[i] for o in outs], dim=0) for i in range(3))

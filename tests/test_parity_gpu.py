@@ -288,3 +288,22 @@ def test_full_size_properties_config5_slice(variant):
     # a 64-query slice against the C oracle, full width
     oi, od = orc.c_knn2(q[:64], t)
     assert np.array_equal(i[:64], oi) and np.array_equal(d[:64], od)
+
+
+def test_host_path_chunked_copy_pipeline():
+    """slm_knn2_host cuts train sets of >= 3M rows into 1M-row chunks (H2D on a second stream, every chunk
+    searched as it lands, chunk results merged by global index): same bytes as the oracle, with duplicates
+    planted across chunk boundaries."""
+    nq, nt = 96, 3_300_000
+    t = synth.uniform(nt, 501)
+    rng = np.random.default_rng(502)
+    q = synth.uniform(nq, 503)
+    src = rng.choice(nt, size=nq // 2, replace=False)
+    q[: nq // 2] = t[src] ^ np.packbits(rng.random((nq // 2, 256)) < 0.05, axis=1, bitorder="little")
+    # exact duplicates of a few matched rows in other chunks, at higher AND lower indices
+    t[(src[:8] + 1_048_576) % nt] = t[src[:8]]
+    t[(src[8:16] + 2_200_000) % nt] = t[src[8:16]]
+    i, d, acc = slammatch.knn2(q, t, ratio=(7, 10))
+    oi, od = orc.c_knn2(q, t)
+    assert np.array_equal(i, oi) and np.array_equal(d, od)
+    assert np.array_equal(acc, orc.c_ratio(od, 7, 10))

@@ -47,11 +47,15 @@ def _worker(rank, world, port, q, t, out_dir):
         def merge(g):
             keys = orc.np_merge_top2(g.numpy().view(np.uint64))
             idx, dd = orc.keys_to_idx_dist(keys)
-            return idx, dd, orc.np_ratio(dd, 7, 10)
+            return torch.from_numpy(idx), torch.from_numpy(dd), torch.from_numpy(orc.np_ratio(dd, 7, 10))
 
         sm = ShardedMatcher(torch.from_numpy(shard), a, local_keys=local_keys, merge=merge)
         assert sm.world == world
         idx, dd, acc = sm.knn2(torch.from_numpy(q))
+        # batched form (config 4 path): the all-gather of batch b overlaps the search of batch b+1
+        bi, bd, ba = sm.knn2(torch.from_numpy(q), query_batch=50)
+        assert np.array_equal(np.asarray(bi), np.asarray(idx)) and np.array_equal(np.asarray(bd), np.asarray(dd))
+        assert np.array_equal(np.asarray(ba), np.asarray(acc))
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx, dist=dd, acc=acc)
     finally:
         dist.destroy_process_group()
