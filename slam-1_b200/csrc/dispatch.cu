@@ -30,8 +30,3 @@ int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_fram
     return SLM_OK;
 }
 
-// Placeholders until the variants land (they fail loudly; nothing falls back silently).
-int slm_bmma_knn2_keys(slm_ctx *, const uint32_t *, int64_t, const uint32_t *, int64_t, int64_t, uint64_t *, cudaStream_t)
-{
-    return slm_fail(SLM_ERR_UNSUPPORTED, "SLM_VARIANT_BMMA is not built in this library");
-}

@@ -131,6 +131,131 @@ __global__ void __launch_bounds__(kThreads) knn2_popc_kernel(PopcParams p)
     }
 }
 
+
+// =====================================================================================================
+// Variant B: b1 AND.POPC mma.sync tiles (north_star part (2), kept for the A/B against LOP3+POPC).
+//   Hamming(a, b) = popc(a) + popc(b) - 2 * popc(a & b);  popc(a & b) comes from
+//   mma.sync.aligned.m16n8k256.row.col.s32.b1.b1.s32.and.popc.
+// On sm_100a ptxas has no native binary MMA: every such instruction is lowered to 8 IMMA.16832 plus ~100
+// logic / move instructions that expand bits to bytes per instruction, so this arm measures
+// "legacy int8 tensor path behind a per-MMA bit expansion".  Same partial-key format and merge kernel as
+// variant P.  Each warp owns 32 queries (two m16 tiles, A fragments register-resident); the 4 lanes of a
+// quad hold different train columns, so the per-row top-2 is finished with two quad shuffles.
+// =====================================================================================================
+constexpr int kBmmaQueriesPerCta = 128;      // 4 warps x 32 queries
+constexpr int kBmmaRowWords = 12;            // 48-byte padded train rows: conflict-free B-fragment loads
+
+__device__ __forceinline__ void bmma_and_popc(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k256.row.col.s32.b1.b1.s32.and.popc "
+                 "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kThreads) knn2_bmma_kernel(PopcParams p)
+{
+    __shared__ __align__(16) uint32_t tile[2][kTileRows * kBmmaRowWords];
+    __shared__ int tile_popc[2][kTileRows];
+
+    const uint32_t *q = p.q;
+    const uint32_t *t = p.t;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+    const int q0 = blockIdx.x * kBmmaQueriesPerCta + warp * 32;
+    const int split = blockIdx.y;
+    const int row_begin = split * p.rows_per_split;
+    const int row_end = min(p.nt, row_begin + p.rows_per_split);
+    const int n_rows = row_end - row_begin;
+
+    // A fragments: tile m covers query rows q0 + 16 m + {g, g + 8}; register i holds words {tg, 4 + tg}
+    uint32_t a[2][4];
+    int pa[2][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int qi = min(q0 + 16 * m + g + 8 * h, p.nq - 1);
+            const uint32_t *row = q + (long long)qi * 8;
+            a[m][h] = __ldg(row + tg);
+            a[m][2 + h] = __ldg(row + 4 + tg);
+            int pc = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) pc += __popc(__ldg(row + w));
+            pa[m][h] = pc;
+        }
+    }
+    unsigned b1[2][2], b2[2][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { b1[m][h] = kLocalNone; b2[m][h] = kLocalNone; }
+
+    const uint4 *tsrc = reinterpret_cast<const uint4 *>(t) + (long long)row_begin * 2;
+    const int n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+    const int last_row = n_rows - 1;
+    auto load_tile = [&](int it, int buf) {
+        // thread r copies train row r of the tile (two 16-byte pieces) and records its popcount
+        const int r = min(it * kTileRows + tid, last_row);
+        const uint4 lo = __ldg(tsrc + 2 * r), hi = __ldg(tsrc + 2 * r + 1);
+        uint4 *dst = reinterpret_cast<uint4 *>(&tile[buf][tid * kBmmaRowWords]);
+        dst[0] = lo;
+        dst[1] = hi;
+        tile_popc[buf][tid] = __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) +
+                              __popc(hi.z) + __popc(hi.w);
+    };
+
+    load_tile(0, 0);
+    __syncthreads();
+    for (int it = 0; it < n_tiles; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < n_tiles) load_tile(it + 1, buf ^ 1);
+        const int rows = min(kTileRows, n_rows - it * kTileRows);
+        const unsigned j0 = (unsigned)(it * kTileRows);
+        for (int n0 = 0; n0 < rows; n0 += 8) {
+            // B fragment: train column n0 + g, words {tg, 4 + tg}
+            const uint32_t *brow = &tile[buf][(n0 + g) * kBmmaRowWords];
+            const uint32_t bf0 = brow[tg], bf1 = brow[4 + tg];
+            const int2 pb = *reinterpret_cast<const int2 *>(&tile_popc[buf][n0 + 2 * tg]);
+            const bool v0 = n0 + 2 * tg < rows, v1 = n0 + 2 * tg + 1 < rows;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                int c[4] = {0, 0, 0, 0};
+                bmma_and_popc(c, a[m], bf0, bf1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const unsigned d = (unsigned)(pa[m][h] + (e ? pb.y : pb.x) - 2 * c[2 * h + e]);
+                        unsigned key = (d << kIdxBits) + (j0 + (unsigned)(n0 + 2 * tg + e));
+                        key = (e ? v1 : v0) ? key : kLocalNone;
+                        const unsigned mx = max(b1[m][h], key);
+                        b1[m][h] = min(b1[m][h], key);
+                        b2[m][h] = min(b2[m][h], mx);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // finish the per-row top-2 across the 4 lanes of a quad
+    unsigned *part = p.part + ((long long)blockIdx.z * p.n_splits + split) * (long long)p.nq * 2;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            unsigned k1 = b1[m][h], k2 = b2[m][h];
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const unsigned o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
+                const unsigned mx = max(k1, o1);
+                k1 = min(k1, o1);
+                k2 = min(min(k2, o2), mx);
+            }
+            const int qi = q0 + 16 * m + g + 8 * h;
+            if (tg == 0 && qi < p.nq) reinterpret_cast<uint2 *>(part)[qi] = make_uint2(k1, k2);
+        }
+}
+
 // Merge the per-split 32-bit local keys into 64-bit global keys.  One thread per (problem, query).
 __global__ void popc_merge_kernel(const unsigned *part, int n_prob, int nq, int n_splits, int rows_per_split,
                                   long long base, unsigned long long *keys_out)
@@ -157,10 +282,12 @@ __global__ void popc_merge_kernel(const unsigned *part, int n_prob, int nq, int 
     reinterpret_cast<ulonglong2 *>(keys_out)[gid] = make_ulonglong2(k1, k2);
 }
 
-int popc_launch(slm_ctx *ctx, PopcParams p, int n_prob, long long base, uint64_t *keys_out, cudaStream_t stream)
+int popc_launch(slm_ctx *ctx, PopcParams p, int n_prob, long long base, uint64_t *keys_out, cudaStream_t stream,
+                bool bmma = false)
 {
-    ctx->last_variant = SLM_VARIANT_POPC;
-    const int qblocks = (p.nq + kQueriesPerCta - 1) / kQueriesPerCta;
+    ctx->last_variant = bmma ? SLM_VARIANT_BMMA : SLM_VARIANT_POPC;
+    const int per_cta = bmma ? kBmmaQueriesPerCta : kQueriesPerCta;
+    const int qblocks = (p.nq + per_cta - 1) / per_cta;
     // enough CTAs for ~8 resident per SM; never split below one tile; local index must fit kIdxBits
     long long target = (long long)ctx->sm_count * 8;
     long long splits = (target + (long long)qblocks * n_prob - 1) / ((long long)qblocks * n_prob);
@@ -182,7 +309,10 @@ int popc_launch(slm_ctx *ctx, PopcParams p, int n_prob, long long base, uint64_t
 
     dim3 grid(qblocks, (unsigned)splits, n_prob);
     SLM_TRY(slm_prof_begin(ctx, stream));
-    knn2_popc_kernel<<<grid, kThreads, 0, stream>>>(p);
+    if (bmma)
+        knn2_bmma_kernel<<<grid, kThreads, 0, stream>>>(p);
+    else
+        knn2_popc_kernel<<<grid, kThreads, 0, stream>>>(p);
     SLM_CUDA(cudaGetLastError());
     SLM_TRY(slm_prof_end(ctx, stream));
     long long total = (long long)n_prob * p.nq;
@@ -203,6 +333,15 @@ int slm_popc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
     p.q = q; p.t = t; p.desc = nullptr; p.pairs = nullptr; p.frame_words = 0;
     p.nq = (int)nq; p.nt = (int)nt;
     return popc_launch(ctx, p, 1, base, keys_out, stream);
+}
+
+int slm_bmma_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                       uint64_t *keys_out, cudaStream_t stream)
+{
+    PopcParams p{};
+    p.q = q; p.t = t; p.desc = nullptr; p.pairs = nullptr; p.frame_words = 0;
+    p.nq = (int)nq; p.nt = (int)nt;
+    return popc_launch(ctx, p, 1, base, keys_out, stream, true);
 }
 
 int slm_popc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame,
