@@ -385,14 +385,28 @@ def ours(args, w, cfg_id):
                                   % (bf16, "MEASURED_PEAKS.json" if peaks else "fallback", macs, sms, clk_mhz)),
                     "frac_vs_2x_bf16_measured": (ach / (2.0 * bf16)) if ach else None,
                     "algorithmic_unit": "1 cmp = 512 fp8 flop (256-bit +-1 dot product)"}
+        elif variant == "bmma":
+            # b1 mma.sync is emulated by ptxas on sm_100a (8 IMMA + ~100 logic/move instructions per MMA): the
+            # kernel is issue-slot-bound (ncu: issue active 70 %, legacy tensor pipe 30 %), no single pipe peak applies
+            ach = cmp_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
+            roof = {"bound": "issue_slots(b1 mma.sync emulation)", "achieved": ach, "peak": None, "unit": "Tcmp/s",
+                    "frac": None, "traffic": None, "kernel": "knn2_bmma_kernel", "kernel_ms": kern_avg_ms,
+                    "peak_note": "no native b1 tensor instruction on sm_100a; see profiles/r1_ncu_bmma_c5.txt"}
         else:
-            # integer pipe: 8 POPC32 per comparison; peak from the micro-benchmark (profiles/), 16 POPC/clk/SM nominal
-            popc_rate = 16.0 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6
+            # integer pipe: 8 POPC32 per comparison on the XU pipe; measured 15.8 lanes/clk/SM (profiles/r1_pipe_rates.txt)
+            probe = {}
+            try:
+                probe = json.load(open(os.path.join(ROOT, "profiles", "peaks_probe.json")))
+            except Exception:
+                pass
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            popc_rate = probe.get("popc32_lanes_per_clk_per_sm", 16.0) * sms * (clocks.get("sm_max_mhz") or 1965.0) * 1e6
             ach = cmp_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
             peak = popc_rate / 8 / 1e12
-            roof = {"bound": "int_popc", "achieved": ach, "peak": peak, "unit": "Tcmp/s",
+            roof = {"bound": "int_popc(xu pipe)", "achieved": ach, "peak": peak, "unit": "Tcmp/s",
                     "frac": (ach / peak) if ach else None, "traffic": None, "kernel": "knn2_popc_kernel",
-                    "kernel_ms": kern_avg_ms, "peak_note": "16 POPC32/clk/SM x 148 SMs x sampled SM clock / 8 POPC per cmp"}
+                    "kernel_ms": kern_avg_ms,
+                    "peak_note": "measured POPC32 lanes/clk/SM (own probe) x SMs x max SM clock / 8 POPC per cmp"}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
