@@ -46,6 +46,11 @@ WORKLOADS = {
                ratio=None, cross=True, sharded=False),
     "c1": dict(name="c1 frame-to-frame: 1000 x 1000, kNN-2 + ratio 0.75", nq=1000, nt=1000, ratio=(3, 4),
                cross=False, sharded=False),
+    # degenerate small-query streaming shapes for north_star's HBM clause
+    "h1": dict(name="h1 streaming: 1 query x 10M descriptors (HBM-bound)", nq=1, nt=10_000_000, ratio=(7, 10),
+               cross=False, sharded=False),
+    "h4": dict(name="h4 streaming: 4 queries x 10M descriptors (HBM/POPC crossover)", nq=4, nt=10_000_000,
+               ratio=(7, 10), cross=False, sharded=False),
 }
 BLOCK = 1_000_000   # synthetic train rows are generated in seeded 1M-row blocks
 
@@ -385,6 +390,15 @@ def ours(args, w, cfg_id):
                                   % (bf16, "MEASURED_PEAKS.json" if peaks else "fallback", macs, sms, clk_mhz)),
                     "frac_vs_2x_bf16_measured": (ach / (2.0 * bf16)) if ach else None,
                     "algorithmic_unit": "1 cmp = 512 fp8 flop (256-bit +-1 dot product)"}
+        elif nq <= 8 and variant == "popc" and args.variant == "auto":
+            # nq <= 8 runs knn2_stream_kernel: the train set streams through the SMs once
+            alg_bytes = 32.0 * (nq + nt / (world if sharded else 1)) + 16.0 * nq
+            ach = alg_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else None
+            peak = peaks.get("hbm_gbs", 6650.0)
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                    "traffic": None, "kernel": "knn2_stream_kernel", "kernel_ms": kern_avg_ms,
+                    "peak_note": ("measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s"),
+                    "algorithmic_bytes": alg_bytes}
         elif variant == "bmma":
             # b1 mma.sync is emulated by ptxas on sm_100a (8 IMMA + ~100 logic/move instructions per MMA): the
             # kernel is issue-slot-bound (ncu: issue active 70 %, legacy tensor pipe 30 %), no single pipe peak applies
@@ -464,7 +478,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
-    cfg_id = int(args.workload[1])
+    cfg_id = int(args.workload[1]) + (5 if args.workload[0] == "h" else 0)
     if args.impl == "reference":
         reference_arm(args, w, cfg_id)
     else:

@@ -8,6 +8,8 @@ int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
 {
     // The tensor-pipe variant is ~9x faster at scale; the integer-pipe variant has the smaller
     // fixed cost, which wins only for tiny problems.
+    // a handful of queries against a long train set is HBM-bound: stream the train rows once
+    if (nq <= 8) return slm_stream_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
     if (nq * nt < kAutoTensorMinCmp) return slm_popc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
     return slm_tc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
 }

@@ -89,6 +89,10 @@ int slm_popc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per
                                const int32_t *pairs_dev, int64_t n_pairs, uint64_t *keys_out,
                                cudaStream_t stream);
 
+// ---- streaming kernel for nq <= 8 (HBM-bound shapes; knn2_stream.cu) -------------------------------------
+int slm_stream_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
+                         int64_t base, uint64_t *keys_out, cudaStream_t stream);
+
 // ---- finalize / merge / compaction (finalize.cu) -------------------------------------------------
 // keys uint64[n][2] -> idx/dist/accept.  rev_keys (optional) = reverse search keys uint64[nt][2] used
 // for the cross-check; train_index_base is subtracted from the forward index to address it.
