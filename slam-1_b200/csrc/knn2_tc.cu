@@ -320,7 +320,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
     auto tiles_in_range = [&](int r) { return min(p.range_tiles, total_tiles - r * p.range_tiles); };
 
     if (tid == 0) {
-        tc::mbar_init(&bars->a_full, 2 * kExp2Threads);
+        tc::mbar_init(&bars->a_full, 2 * kThreads2);
         for (int s = 0; s < kBStages2; ++s) {
             tc::mbar_init(&bars->b_full[s], 2 * kExp2Threads);
             tc::mbar_init(&bars->b_empty[s], 1);
@@ -337,6 +337,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
     tc::cluster_sync();          // barrier inits + TMEM allocation visible to both CTAs
     tc::tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
+
+    // Query tiles: expanded once per cluster by ALL threads (loads issued first, then the expansion), so the
+    // start-up phase is short -- it is pure overhead on the sharded path, where one launch lasts ~0.3 ms.
+    {
+        const uint32_t sA_addr = tc::smem_u32(sA);
+        const int n_rows = mt_mine * kTileM;
+        constexpr int kPer = (kMaxMT2 * kTileM + kThreads2 - 1) / kThreads2;   // 2 rows per thread at most
+        uint4 d0[kPer], d1[kPer];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const int r = tid + i * kThreads2;
+            if (r < n_rows) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(q + (long long)min(q_first + r, p.nq - 1) * 8);
+                d0[i] = __ldg(src);
+                d1[i] = __ldg(src + 1);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const int r = tid + i * kThreads2;
+            if (r < n_rows) tc::expand_row_to_smem(sA_addr + (uint32_t)(r / kTileM) * kATileBytes, r % kTileM, d0[i], d1[i]);
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive_cluster(&bars->a_full, 0);
+    }
 
     if (warp < kEpiWarps) {
         // ===================== epilogue (own TMEM: own 128 query rows x 256 train columns) =====================
@@ -427,17 +452,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
         for (; epoch < p.n_epochs; ++epoch) flush(epoch);     // remaining epochs are written as "none"
     } else if (warp < mma_warp) {
         // ===================== expanders: this CTA's query tiles + its half of every train tile =====================
-        const int et = tid - kEpiThreads;   // 0..127
-        const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
-        for (int r = et; r < mt_mine * kTileM; r += kExp2Threads) {
-            const int qi = min(q_first + r, p.nq - 1);
-            const uint4 *src = reinterpret_cast<const uint4 *>(q + (long long)qi * 8);
-            uint4 d0 = __ldg(src), d1 = __ldg(src + 1);
-            tc::expand_row_to_smem(sA_addr + (uint32_t)(r / kTileM) * kATileBytes, r % kTileM, d0, d1);
-        }
-        tc::fence_proxy_async();
-        tc::mbar_arrive_cluster(&bars->a_full, 0);
-
+        const int et = tid - kEpiThreads;   // 0..95
+        const uint32_t sB_addr = tc::smem_u32(sB);
         // 128 rows per half tile over 96 threads: thread et expands row et, threads 0..31 also row 96 + et
         const bool two_rows = et < 128 - kExp2Threads;
         auto load_row = [&](int r, int bt, int row_in_half, uint4 &d0, uint4 &d1) {
@@ -689,7 +705,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         // Clusters per unit: minimise  waves x (start-up + tiles per cluster x cycles per tile)  with
         // waves = ceil(units * cpg / cluster slots).  Few units (long train sets) end up as one resident wave,
         // many units as several waves of longer-lived clusters.
-        const double kStartupClk = 6000.0, kTileClk = 1024.0 * p.mt;
+        const double kStartupClk = 14000.0, kTileClk = 1024.0 * p.mt;
         long long cpg = 1;
         double best = 1e300;
         const long long cpg_max = n_tiles < 4 * slots ? n_tiles : 4 * slots;
