@@ -1,0 +1,16 @@
+#!/bin/bash
+# Dump SASS listings (instruction text, no encodings) of the hot kernels from the built library.
+cd "$(dirname "$0")/.."
+LIB=slam-1_b200/libslammatch.so
+dump() {  # $1 = substring of the mangled name, $2 = output file
+  cuobjdump -sass $LIB | awk -v pat="$1" '/Function : /{f = index($0, pat) > 0} f{print}' \
+    | grep -E "Function :|^\s+/\*[0-9a-f]{4}\*/" | sed -E 's#/\* 0x[0-9a-f]+ \*/##; s/[ \t]+$//' > profiles/sass/$2
+  echo "$2: $(wc -l < profiles/sass/$2) lines"
+}
+dump "knn2_tc2_kernelILi4" r1_knn2_tc2_kernel_mt4.sass
+dump "knn2_tc_kernelILi1" r1_knn2_tc_kernel_mt1.sass
+dump "knn2_popc_kernel" r1_knn2_popc_kernel.sass
+dump "knn2_bmma_kernel" r1_knn2_bmma_kernel.sass
+dump "knn2_stream_kernelILi1" r1_knn2_stream_kernel_nq1.sass
+dump "tc_refine_kernelILi32" r1_tc_refine_kernel_g32.sass
+grep -c "UTCQMMA" profiles/sass/r1_knn2_tc2_kernel_mt4.sass
