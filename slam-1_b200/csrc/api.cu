@@ -156,7 +156,15 @@ int slm_create(int device, slm_ctx **ctx_out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->force_1cta = getenv("SLM_TC_1CTA") != nullptr;
-    ctx->trace = getenv("SLM_TRACE") != nullptr;   // A/B switch: single-CTA tcgen05 kernel only
+    ctx->trace = getenv("SLM_TRACE") != nullptr;
+    if (const char *e = getenv("SLM_TC_MAX_CPG")) {
+        int v = atoi(e);
+        if (v >= 1) ctx->max_cpg = v;
+    }
+    if (const char *e = getenv("SLM_TC_EPOCH_TILES")) {
+        int v = atoi(e);
+        if (v >= 8 && v <= 4096) ctx->epoch_tiles = v;
+    }   // A/B switch: single-CTA tcgen05 kernel only
     SLM_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming));

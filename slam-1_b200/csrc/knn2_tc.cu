@@ -708,7 +708,8 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         const double kStartupClk = 14000.0, kTileClk = 1024.0 * p.mt;
         long long cpg = 1;
         double best = 1e300;
-        const long long cpg_max = n_tiles < 4 * slots ? n_tiles : 4 * slots;
+        long long cpg_max = n_tiles < 4 * slots ? n_tiles : 4 * slots;
+        if (cpg_max > ctx->max_cpg) cpg_max = ctx->max_cpg;
         for (long long c = 1; c <= cpg_max; ++c) {
             const long long waves = (units * c + slots - 1) / slots;
             const double cost = (double)waves * (kStartupClk + (double)((n_tiles + c - 1) / c) * kTileClk);
@@ -718,7 +719,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         if (range_tiles < 1) range_tiles = 1;
         if (range_tiles > 8) range_tiles = 8;
         const long long n_ranges = (n_tiles + range_tiles - 1) / range_tiles;
-        const long long rpe = kMaxEpochTiles / range_tiles;
+        const long long rpe = ctx->epoch_tiles / range_tiles;      // <= kMaxEpochTiles tiles per epoch
         const long long ranges_per_unit = (n_ranges + cpg - 1) / cpg;
         p.cpg = (int)cpg;
         p.range_tiles = (int)range_tiles;

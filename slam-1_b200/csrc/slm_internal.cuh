@@ -21,6 +21,8 @@ struct slm_ctx {
     int sm_count = 148;
     int variant = SLM_VARIANT_AUTO;
     int last_variant = 0;
+    int epoch_tiles = 4096;   // tiles per candidate epoch (SLM_TC_EPOCH_TILES shrinks it so tests reach the epoch logic)
+    int max_cpg = 1 << 30;    // cap on clusters per query-group pair (SLM_TC_MAX_CPG, tests only)
     int force_1cta = 0;   // debugging / A-B: run the single-CTA tcgen05 kernel even when CTA pairs apply
     int64_t launches = 0;
     // device buffers owned by the ctx, each grown on demand (never shrunk)

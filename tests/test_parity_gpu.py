@@ -307,3 +307,28 @@ def test_host_path_chunked_copy_pipeline():
     oi, od = orc.c_knn2(q, t)
     assert np.array_equal(i, oi) and np.array_equal(d, od)
     assert np.array_equal(acc, orc.c_ratio(od, 7, 10))
+
+
+def test_candidate_epochs_of_resident_clusters():
+    """A resident cluster that walks more than 4096 tiles (1M rows) flushes its candidates in epochs.  The
+    limit is lowered through SLM_TC_EPOCH_TILES in a fresh process so a 40k-row train set exercises it."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, 'slam-1_b200'); sys.path.insert(0, '.')
+import slammatch
+from slammatch import synth
+from oracle import oracle as orc
+q, t = synth.planted(300, 40000, 321)
+t = synth.with_duplicates(t, 322, 0.3)
+i, d, a = slammatch.knn2(q, t, ratio=(7, 10), variant='tensor')
+oi, od = orc.c_knn2(q, t)
+assert np.array_equal(i, oi) and np.array_equal(d, od)
+assert np.array_equal(a, orc.c_ratio(od, 7, 10))
+print('EPOCH_OK')
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SLM_TC_EPOCH_TILES="8", SLM_TC_MAX_CPG="3")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert "EPOCH_OK" in r.stdout, r.stdout + r.stderr
