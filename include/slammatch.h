@@ -147,6 +147,29 @@ int slm_compact_matches(slm_ctx *ctx, const int32_t *idx_dev, const int32_t *dis
                         int32_t *matches_out_dev, int32_t *count_out_dev, void *stream);
 
 /*
+ * Device-side gather driven by the compacted match list (the list comprehensions at tracking.py:32-33,
+ * keypoint.py:53-57, Point3D.py:50-52): out[m] = src[matches[m][column]] for m < *count_dev, rows of
+ * row_bytes bytes (a multiple of 4: keypoint coordinates float32[.][2] -> 8, descriptors -> 32, 3-D points
+ * float64[.][3] -> 24).  column 0 gathers by queryIdx, 1 by trainIdx.  out_dev must hold capacity rows.
+ */
+int slm_gather_rows(slm_ctx *ctx, const void *src_dev, int32_t row_bytes, const int32_t *matches_dev,
+                    const int32_t *count_dev, int64_t capacity, int32_t column, void *out_dev, void *stream);
+
+/*
+ * Bag-of-words follow-on (bag_of_words.py:23-42).
+ * slm_bow_hist: histogram of word ids, hist_out_dev int32[n_words] (zeroed first).  words_dev holds one word
+ *   id every `stride` int32 (stride 2 reads column 0 of the idx[n][2] result of a word-assignment search);
+ *   equals np.histogram(labels, bins=n_words, range=(0, n_words-1)) for labels in [0, n_words).
+ * slm_chi2_scan: dist_out_dev[i] = sum_w 2*(h[w]-db[i][w])^2 / max(1, h[w]+db[i][w]) in float64 for the n_db stored
+ *   histograms db_dev int32[n_db][n_words], bit-exact with numpy (same division, same pairwise summation
+ *   order), plus best_idx_dev / best_val_dev = (np.argmin, np.min) -- first minimum wins.
+ */
+int slm_bow_hist(slm_ctx *ctx, const int32_t *words_dev, int64_t n, int32_t stride, int32_t n_words,
+                 int32_t *hist_out_dev, void *stream);
+int slm_chi2_scan(slm_ctx *ctx, const int32_t *hist_dev, const int32_t *db_dev, int64_t n_db, int32_t n_words,
+                  double *dist_out_dev, int32_t *best_idx_dev, double *best_val_dev, void *stream);
+
+/*
  * Host-memory convenience: what the Python shim's knnMatch(des1, des2, k=2) calls.  q_host/t_host are
  * uint8[n][32] in host memory (pinned or pageable; pageable memory is staged through the ctx's pinned
  * buffers); outputs are host arrays.  Copies, kernels and the read-back run on the ctx's own stream and

@@ -312,3 +312,27 @@ def cv_cross_check_pairs(q, t):
     import cv2
     m = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(_as_desc(q), _as_desc(t))
     return sorted((x.queryIdx, x.trainIdx, int(round(x.distance))) for x in m)
+
+
+# ----------------------------------------------------------------------------------------------
+# Bag-of-words follow-on (bag_of_words.py:23-42), restated with the reference's own numpy expressions
+# ----------------------------------------------------------------------------------------------
+def np_bow_hist(labels, n_clusters: int) -> np.ndarray:
+    """bag_of_words.py:25: np.histogram(labels, bins=k, range=(0, k - 1))."""
+    hist, _ = np.histogram(np.asarray(labels), bins=n_clusters, range=(0, n_clusters - 1))
+    return hist
+
+
+def np_chi2(x, y) -> float:
+    """bag_of_words.py:30-31 (and :47-48)."""
+    return np.sum(2 * (x - y) ** 2 / (np.maximum(1, x + y)))
+
+
+def np_predict_previous(h, db, img_index: int, threshold: int):
+    """bag_of_words.py:33-42 with the histogram already computed."""
+    if img_index < threshold:
+        return -1, -1
+    dist = []
+    for i in range(0, (img_index + 1 - threshold)):
+        dist.append(np_chi2(h, db[i]))
+    return np.argmin(dist), np.min(dist)

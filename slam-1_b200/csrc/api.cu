@@ -338,6 +338,39 @@ int slm_compact_matches(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, c
     return slm_compact(ctx, idx, dist, accept, nq, stop_at_short_row, matches_out, count_out, (cudaStream_t)stream);
 }
 
+int slm_gather_rows(slm_ctx *ctx, const void *src, int32_t row_bytes, const int32_t *matches, const int32_t *count,
+                    int64_t capacity, int32_t column, void *out, void *stream)
+{
+    SLM_TRY(check_ctx(ctx));
+    if (row_bytes <= 0 || (row_bytes & 3)) return slm_fail(SLM_ERR_INVALID, "row_bytes must be a positive multiple of 4");
+    if (column != 0 && column != 1) return slm_fail(SLM_ERR_INVALID, "column must be 0 (queryIdx) or 1 (trainIdx)");
+    if (capacity < 0) return slm_fail(SLM_ERR_INVALID, "negative capacity");
+    if (capacity == 0) return SLM_OK;
+    if (!src || !matches || !count || !out) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    return slm_gather(ctx, src, row_bytes, matches, count, capacity, column, out, (cudaStream_t)stream);
+}
+
+int slm_bow_hist(slm_ctx *ctx, const int32_t *words, int64_t n, int32_t stride, int32_t n_words, int32_t *hist_out,
+                 void *stream)
+{
+    SLM_TRY(check_ctx(ctx));
+    if (n < 0 || stride < 1 || n_words < 1) return slm_fail(SLM_ERR_INVALID, "bad size (n=%lld stride=%d n_words=%d)",
+                                                              (long long)n, stride, n_words);
+    if (!hist_out || (n > 0 && !words)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    return slm_bow_hist_impl(ctx, words, n, stride, n_words, hist_out, (cudaStream_t)stream);
+}
+
+int slm_chi2_scan(slm_ctx *ctx, const int32_t *hist, const int32_t *db, int64_t n_db, int32_t n_words, double *dist_out,
+                  int32_t *best_idx, double *best_val, void *stream)
+{
+    SLM_TRY(check_ctx(ctx));
+    if (n_db < 0 || n_words < 1 || n_words > 12288) return slm_fail(SLM_ERR_INVALID, "bad size (n_db=%lld n_words=%d)",
+                                                                      (long long)n_db, n_words);
+    if (n_db == 0) return SLM_OK;
+    if (!hist || !db || !dist_out || !best_idx || !best_val) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    return slm_chi2_scan_impl(ctx, hist, db, n_db, n_words, dist_out, best_idx, best_val, (cudaStream_t)stream);
+}
+
 int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t *t_host, int64_t nt,
                   int32_t ratio_num, int32_t ratio_den, int32_t cross_check, int32_t *idx_out,
                   int32_t *dist_out, uint8_t *accept_out)

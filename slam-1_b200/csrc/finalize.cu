@@ -128,7 +128,33 @@ compact_kernel(const int *idx, const int *dist, const unsigned char *accept, lon
     if (tid == 0) *count_out = chunk_base;
 }
 
+// out[m] = src[matches[m][column]] in 4-byte words; one thread per output word.
+__global__ void gather_rows_kernel(const unsigned *src, int row_words, const int *matches, const int *count,
+                                   long long capacity, int column, unsigned *out)
+{
+    const long long n = min((long long)*count, capacity) * row_words;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / row_words;
+        const int w = (int)(i % row_words);
+        out[i] = src[(long long)matches[3 * m + column] * row_words + w];
+    }
+}
+
 }  // namespace
+
+int slm_gather(slm_ctx *ctx, const void *src, int32_t row_bytes, const int32_t *matches, const int32_t *count,
+               int64_t capacity, int32_t column, void *out, cudaStream_t stream)
+{
+    if (capacity <= 0) return SLM_OK;
+    const int row_words = row_bytes / 4;
+    long long blocks = (capacity * row_words + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    gather_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const unsigned *>(src), row_words, matches,
+                                                             count, capacity, column, reinterpret_cast<unsigned *>(out));
+    SLM_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SLM_OK;
+}
 
 int slm_finalize(slm_ctx *ctx, const uint64_t *keys, int64_t n, int32_t ratio_num, int32_t ratio_den,
                  const uint64_t *rev_keys, int64_t nt, int64_t train_index_base, int32_t *idx_out,

@@ -105,6 +105,8 @@ int slm_merge_keys(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int
                    uint64_t *keys_out, cudaStream_t stream);
 int slm_merge_finalize(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int64_t nq, int32_t ratio_num,
                        int32_t ratio_den, int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
+int slm_gather(slm_ctx *ctx, const void *src, int32_t row_bytes, const int32_t *matches, const int32_t *count,
+               int64_t capacity, int32_t column, void *out, cudaStream_t stream);
 int slm_compact(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
                 int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, cudaStream_t stream);
 
@@ -123,3 +125,9 @@ int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
                        int64_t base, uint64_t *keys_out, cudaStream_t stream);
 int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
                           int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream);
+
+// ---- bag-of-words follow-on (bow.cu) ------------------------------------------------------------------
+int slm_bow_hist_impl(slm_ctx *ctx, const int32_t *idx, int64_t n, int32_t idx_stride, int32_t n_words, int32_t *hist,
+                      cudaStream_t stream);
+int slm_chi2_scan_impl(slm_ctx *ctx, const int32_t *hq, const int32_t *db, int64_t n_db, int32_t k, double *dist,
+                       int32_t *best_idx, double *best_val, cudaStream_t stream);

@@ -8,8 +8,8 @@ libslammatch.so (hand-written CUDA for sm_100a behind the C-ABI of include/slamm
 """
 from . import synth  # noqa: F401  (pure numpy; safe without a GPU)
 from ._lib import SlamMatchError, Context, context, load, LIB_PATH, SYMBOLS, VARIANTS  # noqa: F401
-from .matcher import (DMatch, Matcher, REFERENCE_RATIO, get_matches, good_matches, install, knn2,  # noqa: F401
-                      uninstall)
+from .matcher import (DMatch, Matcher, REFERENCE_RATIO, get_matches, get_matches_device, good_matches,  # noqa: F401
+                      install, knn2, uninstall)
 
-__all__ = ["Matcher", "DMatch", "knn2", "install", "uninstall", "get_matches", "good_matches", "context",
+__all__ = ["Matcher", "DMatch", "knn2", "install", "uninstall", "get_matches", "get_matches_device", "good_matches", "context",
            "Context", "SlamMatchError", "load", "synth", "REFERENCE_RATIO"]

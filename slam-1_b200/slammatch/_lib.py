@@ -21,7 +21,8 @@ SYMBOLS = (
     "slm_launch_count",
     "slm_profile_enable", "slm_profile_read",
     "slm_knn2", "slm_knn2_keys", "slm_knn2_filter", "slm_knn2_batched", "slm_merge_top2",
-    "slm_compact_matches", "slm_knn2_host",
+    "slm_compact_matches", "slm_gather_rows", "slm_bow_hist", "slm_chi2_scan",
+    "slm_knn2_host",
 )
 
 _lib = None
@@ -68,6 +69,9 @@ def load():
         lib.slm_knn2_batched.argtypes = [vp, vp, i64, i64, vp, i64, i32, i32, vp, vp, vp, vp]
         lib.slm_merge_top2.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, vp]
         lib.slm_compact_matches.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
+        lib.slm_gather_rows.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp, vp]
+        lib.slm_bow_hist.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+        lib.slm_chi2_scan.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp]
         lib.slm_knn2_host.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]
         for name in SYMBOLS:
             if name not in ("slm_last_error", "slm_launch_count"):

@@ -264,3 +264,30 @@ def get_matches(kp1_pts, des1, kp2_pts, des2, device: int = 0):
     q1 = np.float32(np.asarray(kp1_pts)[rows])
     q2 = np.float32(np.asarray(kp2_pts)[tidx])
     return q1, q2
+
+
+def get_matches_device(kp1_xy, des1, kp2_xy, des2, ratio=REFERENCE_RATIO):
+    """tracking.get_matches (tracking.py:12-34) with everything device-resident: descriptors ``uint8[n,32]`` and
+    keypoint coordinates ``float32[n,2]`` are CUDA tensors; the search, the ratio loop (with its truncation at the
+    first short row), the compaction of ``good`` and both gathers run on the GPU.  Returns ``(q1, q2)`` CUDA
+    tensors ``float32[M,2]`` -- one 4-byte read-back (M) is the only host synchronisation."""
+    import torch
+    idx, dist, acc = knn2(des1, des2, ratio=ratio)
+    dev, nq = idx.device, idx.shape[0]
+    ctx = _lib.context(dev.index or 0)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    matches = torch.empty((max(nq, 1), 3), dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(ctx.lib.slm_compact_matches(ctx.handle, idx.data_ptr(), dist.data_ptr(), acc.data_ptr(), nq, 1,
+                                           matches.data_ptr(), count.data_ptr(), stream))
+    out = []
+    for col, xy in ((0, kp1_xy), (1, kp2_xy)):
+        xy = xy.contiguous()
+        if xy.dtype != torch.float32 or xy.dim() != 2:
+            raise ValueError("keypoint coordinates must be float32[n, k] CUDA tensors")
+        o = torch.empty((max(nq, 1), xy.shape[1]), dtype=torch.float32, device=dev)
+        _lib.check(ctx.lib.slm_gather_rows(ctx.handle, xy.data_ptr(), 4 * xy.shape[1], matches.data_ptr(),
+                                           count.data_ptr(), nq, col, o.data_ptr(), stream))
+        out.append(o)
+    m = int(count.item())
+    return out[0][:m], out[1][:m]

@@ -1,0 +1,67 @@
+"""Bag-of-words follow-on: word histogram + chi-square scan + argmin against the
+reference's own numpy expressions (bag_of_words.py:23-42), bit-exact including the float64 sums."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from slammatch import synth
+
+
+def test_histogram_binning_of_the_reference_is_the_identity():
+    # np.histogram(labels, bins=k, range=(0, k-1)) == bincount for integer labels in [0, k)  (CPU only)
+    rng = np.random.default_rng(1)
+    for k in (2, 50, 64, 1000):
+        labels = rng.integers(0, k, 5000)
+        assert np.array_equal(orc.np_bow_hist(labels, k), np.bincount(labels, minlength=k))
+
+
+@pytest.mark.gpu
+def test_bow_hist_and_scan_match_reference_arithmetic():
+    from slammatch.bow import BoW
+    for k, n_img, n_desc, seed in ((50, 40, 100, 1), (64, 130, 300, 2), (300, 25, 500, 3), (1000, 12, 800, 4)):
+        vocab = synth.uniform(k, 900 + seed)
+        imgs = [synth.planted(n_desc, k, 1000 * seed + i)[0] for i in range(n_img)]
+        bow = BoW(vocab, capacity=8)                       # small capacity: exercises the growth path
+        bow.train(imgs)
+        db = bow.db
+        assert db.shape == (n_img, k)
+        for i in (0, n_img // 2, n_img - 1):
+            words = orc.c_knn2(imgs[i], vocab)[0][:, 0]
+            want = orc.np_bow_hist(words, k)
+            assert np.array_equal(db[i], want), (k, i)
+            assert np.array_equal(bow.hist(imgs[i]), want)
+        q = synth.planted(n_desc, k, 77 + seed)[0]
+        h = orc.np_bow_hist(orc.c_knn2(q, vocab)[0][:, 0], k)
+        for img_index, thr in ((n_img - 1, 0), (n_img - 1, 5), (10, 3), (2, 5)):
+            want = orc.np_predict_previous(h, db, img_index, thr)
+            got = bow.predict_previous(q, img_index, thr)
+            assert got[0] == want[0], (k, img_index, thr)
+            assert got[1] == want[1], (k, img_index, thr, got, want)      # bit-exact float64
+        i, v = bow.predict(q)
+        dist = [orc.np_chi2(h, e) for e in db]
+        assert (i, v) == (int(np.argmin(dist)), float(np.min(dist)))
+        # an image that is in the db scores exactly 0 against itself and wins with the lowest index
+        i, v = bow.predict(imgs[3])
+        assert v == 0.0 and i == 3
+
+
+@pytest.mark.gpu
+def test_chi2_scan_first_minimum_wins_and_sum_order_is_numpys():
+    import torch
+    from slammatch import _lib
+    ctx = _lib.context(0)
+    rng = np.random.default_rng(9)
+    for k in (5, 8, 50, 129, 300, 1000):
+        n_db = 700
+        db = rng.integers(0, 40, (n_db, k)).astype(np.int32)
+        db[500] = db[20]                                    # exact tie: argmin must report 20
+        h = db[20].copy(); h[:3] += 1
+        want = np.array([orc.np_chi2(h.astype(np.int64), r.astype(np.int64)) for r in db])
+        hd, dd = torch.from_numpy(h).cuda(), torch.from_numpy(db).cuda()
+        dist = torch.empty(n_db, dtype=torch.float64, device="cuda")
+        bi = torch.empty(1, dtype=torch.int32, device="cuda"); bv = torch.empty(1, dtype=torch.float64, device="cuda")
+        _lib.check(ctx.lib.slm_chi2_scan(ctx.handle, hd.data_ptr(), dd.data_ptr(), n_db, k, dist.data_ptr(),
+                                         bi.data_ptr(), bv.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(dist.cpu().numpy(), want), k            # every distance bit-exact
+        assert int(bi.item()) == int(np.argmin(want)) == 20 and float(bv.item()) == float(np.min(want))

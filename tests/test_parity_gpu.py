@@ -332,3 +332,17 @@ print('EPOCH_OK')
     env = dict(os.environ, SLM_TC_EPOCH_TILES="8", SLM_TC_MAX_CPG="3")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert "EPOCH_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_device_resident_get_matches_equals_reference_outputs():
+    """get_matches_device: search + ratio + compaction + gathers on the GPU against the golden outputs of the real
+    tracking.get_matches (tracking.py:12-34)."""
+    import torch
+    z = np.load(os.path.join(GOLDEN, "reference_functions.npz"))
+    for name in z["names"]:
+        name = str(name)
+        des1, des2 = torch.from_numpy(z[name + "/q"]).cuda(), torch.from_numpy(z[name + "/t"]).cuda()
+        p1, p2 = torch.from_numpy(z[name + "/p1"]).cuda(), torch.from_numpy(z[name + "/p2"]).cuda()
+        q1, q2 = slammatch.get_matches_device(p1, des1, p2, des2)
+        assert np.array_equal(q1.cpu().numpy().reshape(-1), z[name + "/gm_q1"].reshape(-1)), name
+        assert np.array_equal(q2.cpu().numpy().reshape(-1), z[name + "/gm_q2"].reshape(-1)), name
