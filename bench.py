@@ -353,6 +353,26 @@ def ours(args, w, cfg_id):
     e2e_val = cmp_per_step * jobs * e2e_steps / float(t_e.item()) / 1e9
     out_bytes = (P * nq if args.workload == "c3" else nq) * 17
 
+    # Same call with the train set held in a persistent device-resident collection (OpenCV's matcher.add([...]) +
+    # knnMatch(q, k) form; slammatch.KeyframeDB): the DB is uploaded once, outside the timed region, and every step
+    # moves only the query descriptors in and the results out.  Reported NEXT TO e2e, never instead of it.
+    resident = None
+    if world == 1 and args.workload in ("c5", "c4"):
+        db = slammatch.KeyframeDB(device=local, capacity=nt)
+        db.add(t_d)
+        qn = q_pin.numpy()
+        for _ in range(2):
+            db.query(qn, ratio=w["ratio"])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            db.query(qn, ratio=w["ratio"])
+        torch.cuda.synchronize(dev)
+        resident = {"value": cmp_per_step * e2e_steps / (time.perf_counter() - t0) / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": int(q_h.nbytes), "d2h_bytes_per_step": int(out_bytes),
+                    "api": "slammatch.KeyframeDB.add(train) once, then .query(host queries) per step"}
+        del db
+
     if rank == 0:
         peaks = {}
         try:
@@ -454,7 +474,8 @@ def ours(args, w, cfg_id):
             "wall_ms_per_step": wall_ms / args.steps,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
                     "steps": e2e_steps, "api": "slammatch.knn2(host arrays) -> slm_knn2_host" if not (sharded or args.workload == "c3")
-                    else "pinned host -> device copy + device entry points + result read-back"},
+                    else "pinned host -> device copy + device entry points + result read-back",
+                    "resident_db": resident},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -11,5 +11,7 @@ from ._lib import SlamMatchError, Context, context, load, LIB_PATH, SYMBOLS, VAR
 from .matcher import (DMatch, Matcher, REFERENCE_RATIO, get_matches, get_matches_device, good_matches,  # noqa: F401
                       install, knn2, uninstall)
 
-__all__ = ["Matcher", "DMatch", "knn2", "install", "uninstall", "get_matches", "get_matches_device", "good_matches", "context",
+from .keyframe_db import KeyframeDB  # noqa: F401,E402
+
+__all__ = ["KeyframeDB", "Matcher", "DMatch", "knn2", "install", "uninstall", "get_matches", "get_matches_device", "good_matches", "context",
            "Context", "SlamMatchError", "load", "synth", "REFERENCE_RATIO"]

@@ -143,14 +143,23 @@ class Matcher:
         self.device = device
         self.variant = variant
         self._train: list[np.ndarray] = []
+        self._db = None     # device-resident copy of the collection, uploaded once in add()
 
     # -- train collection (OpenCV's add([...]) + knnMatch(q, k) form) --------------------------------
     def add(self, descriptors):
+        """``matcher.add([des_a, des_b, ...])``: the collection is uploaded to the GPU once, here, so that
+        later ``knnMatch(q, k)`` calls only move the query (see slammatch.keyframe_db.KeyframeDB)."""
+        from .keyframe_db import KeyframeDB
         for d in descriptors:
-            self._train.append(_as_desc(d, "descriptors"))
+            d = _as_desc(d, "descriptors")
+            self._train.append(d)
+            if self._db is None:
+                self._db = KeyframeDB(self.device)
+            self._db.add(d)
 
     def clear(self):
         self._train = []
+        self._db = None
 
     def empty(self) -> bool:
         return not self._train
@@ -179,6 +188,10 @@ class Matcher:
             # OpenCV: batch_distance.cpp:303 asserts K == 1 when crossCheck is set
             raise ValueError("crossCheck=True requires k == 1 (as in OpenCV); use knn2(cross_check=True) for kNN-2 + cross-check")
         q = _as_desc(queryDescriptors, "queryDescriptors")
+        if trainDescriptors is None and self._db is not None and q.shape[0] > 0:
+            # resident collection: only the query crosses PCIe
+            idx, dist, acc = self._db.query(q, ratio=None, cross_check=self.crossCheck)
+            return self._rows(idx, dist, acc if self.crossCheck else None, k, np.asarray(self._db._offsets))
         if trainDescriptors is None:
             t, offsets = self._collection()
         else:

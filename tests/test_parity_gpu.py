@@ -346,3 +346,45 @@ def test_device_resident_get_matches_equals_reference_outputs():
         q1, q2 = slammatch.get_matches_device(p1, des1, p2, des2)
         assert np.array_equal(q1.cpu().numpy().reshape(-1), z[name + "/gm_q1"].reshape(-1)), name
         assert np.array_equal(q2.cpu().numpy().reshape(-1), z[name + "/gm_q2"].reshape(-1)), name
+
+
+def test_keyframe_db_is_an_append_only_resident_collection():
+    """KeyframeDB == OpenCV's add([...]) + knnMatch(q, k): global row order, (keyframe, local row) mapping,
+    growth of the device array, queries from host and from device memory."""
+    import torch
+    db = slammatch.KeyframeDB(capacity=256)
+    frames = [synth.uniform(n, 700 + i) for i, n in enumerate((300, 1, 257, 1000, 64))]
+    frames[3][10] = frames[0][5]                      # duplicate descriptor in a later keyframe
+    for i, f in enumerate(frames):
+        assert db.add(f) == i
+    flat = np.concatenate(frames)
+    assert len(db) == 5 and db.n_rows == flat.shape[0]
+    assert np.array_equal(db.rows().cpu().numpy(), flat)
+    q = flat[[5, 301, 400, 1600]] ^ np.uint8(1)
+    i, d, a = db.query(q, ratio=(7, 10))
+    oi, od = orc.c_knn2(q, flat)
+    assert np.array_equal(i, oi) and np.array_equal(d, od) and np.array_equal(a, orc.c_ratio(od, 7, 10))
+    kf, loc = db.locate(i[:, 0])
+    assert kf.tolist() == [0, 2, 2, 4] and loc[0] == 5          # lowest global row wins the planted duplicate
+    i2, d2, a2 = db.query(torch.from_numpy(q).cuda(), ratio=(7, 10))
+    assert np.array_equal(i2.cpu().numpy(), oi)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_fuzz(seed, variant):
+    """Random (nq, nt) pairs around tile / chunk / warp boundaries, mixed generators, every variant."""
+    rng = np.random.default_rng(4242 + seed)
+    for _ in range(6):
+        nq = int(rng.choice([1, 2, 7, 8, 9, 31, 33, 127, 128, 129, 255, 257, 383, 385, 511, 513, 1023, 1500]))
+        nt = int(rng.choice([1, 2, 31, 32, 33, 63, 255, 256, 257, 511, 513, 767, 1025, 2047, 4097, 9999, 33000]))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            q, t = synth.uniform(nq, seed * 100 + nq), synth.uniform(nt, seed * 100 + nt + 1)
+        elif kind == 1:
+            q, t = synth.heavy_ties(nq, seed * 100 + nq), synth.heavy_ties(nt, seed * 100 + nt + 1)
+        else:
+            q, t = synth.planted(nq, nt, seed * 100 + nq + nt)
+            t = synth.with_duplicates(t, seed, 0.3)
+        i, d, a = slammatch.knn2(q, t, ratio=(7, 10), cross_check=bool(rng.integers(0, 2)), variant=variant)
+        oi, od = orc.c_knn2(q, t)
+        assert np.array_equal(i, oi) and np.array_equal(d, od), (variant, nq, nt, kind)
