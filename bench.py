@@ -117,6 +117,18 @@ class ClockSampler:
                 pass
             self._stop.wait(0.02)
 
+    def sample_now(self):
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def reset(self):
         self.samples, self.reasons = [], set()
 
@@ -126,6 +138,7 @@ class ClockSampler:
             self._thread.start()
 
     def stop(self):
+        self.sample_now()
         self._stop.set()
         if self._thread:
             self._thread.join()
@@ -302,6 +315,7 @@ def ours(args, w, cfg_id):
         for _ in range(args.steps):
             out = step_device()
         evs[0][1].record()
+        sampler.sample_now()          # the GPU is still working through the queued steps here
         barrier()
         dev_ms = evs[0][0].elapsed_time(evs[0][1])
     else:

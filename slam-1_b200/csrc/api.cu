@@ -324,8 +324,10 @@ int slm_merge_top2(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int
     if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
     if (nq == 0) return SLM_OK;
     if (!gathered) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
-    return slm_merge_finalize(ctx, gathered, n_shards, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out,
-                              (cudaStream_t)stream_);
+    SLM_TRY(slm_prof_mark(ctx, (cudaStream_t)stream_, SLM_TAG_CALL_BEGIN));
+    SLM_TRY(slm_merge_finalize(ctx, gathered, n_shards, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out,
+                               (cudaStream_t)stream_));
+    return slm_prof_mark(ctx, (cudaStream_t)stream_, SLM_TAG_CALL_END);
 }
 
 int slm_compact_matches(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
