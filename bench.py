@@ -266,7 +266,7 @@ def ours(args, w, cfg_id):
         t_d = t_pin.to(dev)
         cmp_per_step = float(nq) * nt            # whole job, all ranks together
         in_bytes = q_h.nbytes + t_h.nbytes
-        sm = ShardedMatcher(t_d, first, ratio=w["ratio"], variant=args.variant)
+        sm = ShardedMatcher(t_d, first, ratio=w["ratio"], variant=args.variant, exchange=args.exchange)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def step_device():
@@ -481,7 +481,7 @@ def ours(args, w, cfg_id):
             "config": {"workload": w["name"], "nq": nq, "nt": nt, "variant": variant, "variant_requested": args.variant,
                        "l2": "inputs larger than L2 (streamed from HBM every step)" if flush is None
                              else "256 MiB L2 flush between timed steps",
-                       "parallelism": (f"train rows sharded over {world} ranks, all-gather of packed top-2 keys + merge"
+                       "parallelism": (f"train rows sharded over {world} ranks, exchange of packed top-2 keys ({sm.exchange}) + merge"
                                        if sharded else ("single GPU" if world == 1 else f"{world} replicas"))},
             "matched_queries_per_s": matched * jobs / (dev_ms / args.steps * 1e-3),
             "matched_per_step": matched,
@@ -510,6 +510,8 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="auto", choices=["auto", "popc", "tensor", "bmma"])
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvlink"],
+                    help="sharded path: how per-rank keys are exchanged (auto = NVLink peer stores when available)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

@@ -136,6 +136,22 @@ int slm_merge_top2(slm_ctx *ctx, const uint64_t *gathered_keys_dev, int32_t n_sh
                    uint8_t *accept_out_dev, void *stream);
 
 /*
+ * NVLink exchange + merge in ONE kernel (the sharded path's replacement for all-gather + slm_merge_top2 when the
+ * gather buffers are peer-mapped, e.g. torch symmetric memory over NVLink / NVSwitch).
+ *   peer_keys_host[r]  : device address, valid on THIS GPU, of rank r's buffer uint64[2][world][nq_capacity][2]
+ *   peer_flags_host[r] : device address of rank r's flag array uint32[2][world] (zero-initialised once)
+ * The kernel stores this rank's nq x 2 keys into slot [step & 1][rank] of every peer's buffer (16-byte stores
+ * over NVLink), publishes `step` into every peer's flag [step & 1][rank] with a system-scope release, waits
+ * (bounded) until its own flags show `step` from every rank, then merges and finalises like slm_merge_top2.
+ * `step` must be the same on all ranks, start at 1 and increase by 1 per call; two buffer halves make the
+ * scheme safe without any other synchronisation.  nq <= 8192 and nq <= nq_capacity.
+ */
+int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys_dev, int64_t nq, int64_t nq_capacity,
+                       const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank, int32_t world,
+                       uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out_dev,
+                       int32_t *dist_out_dev, uint8_t *accept_out_dev, void *stream);
+
+/*
  * Device-side compaction of accepted rows (the gathers at tracking.py:32-33 start from this list):
  * writes (queryIdx, trainIdx, distance) int32 triples in ascending queryIdx order to matches_out_dev
  * (capacity nq triples) and the count to count_out_dev (int32[1]).

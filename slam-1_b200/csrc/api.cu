@@ -330,6 +330,23 @@ int slm_merge_top2(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int
     return slm_prof_mark(ctx, (cudaStream_t)stream_, SLM_TAG_CALL_END);
 }
 
+int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys, int64_t nq, int64_t nq_capacity,
+                       const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank, int32_t world,
+                       uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out, int32_t *dist_out,
+                       uint8_t *accept_out, void *stream)
+{
+    SLM_TRY(check_ctx(ctx));
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return slm_fail(SLM_ERR_INVALID, "bad rank/world (%d/%d)", rank, world);
+    if (nq < 0 || nq > 8192 || nq > nq_capacity) return slm_fail(SLM_ERR_INVALID, "nq must be <= min(8192, nq_capacity)");
+    if (step == 0) return slm_fail(SLM_ERR_INVALID, "step starts at 1");
+    if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
+    if (!peer_keys_host || !peer_flags_host || (nq > 0 && !local_keys)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(slm_prof_mark(ctx, (cudaStream_t)stream, SLM_TAG_CALL_BEGIN));
+    SLM_TRY(slm_exchange_merge_impl(ctx, local_keys, nq, nq_capacity, peer_keys_host, peer_flags_host, rank, world, step,
+                                    ratio_num, ratio_den, idx_out, dist_out, accept_out, (cudaStream_t)stream));
+    return slm_prof_mark(ctx, (cudaStream_t)stream, SLM_TAG_CALL_END);
+}
+
 int slm_compact_matches(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
                         int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, void *stream)
 {

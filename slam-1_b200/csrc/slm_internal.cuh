@@ -107,6 +107,10 @@ int slm_merge_finalize(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards,
                        int32_t ratio_den, int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
 int slm_gather(slm_ctx *ctx, const void *src, int32_t row_bytes, const int32_t *matches, const int32_t *count,
                int64_t capacity, int32_t column, void *out, cudaStream_t stream);
+int slm_exchange_merge_impl(slm_ctx *ctx, const uint64_t *local_keys, int64_t nq, int64_t cap,
+                            const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank, int32_t world,
+                            uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out, int32_t *dist_out,
+                            uint8_t *accept_out, cudaStream_t stream);
 int slm_compact(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
                 int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, cudaStream_t stream);
 

@@ -38,7 +38,7 @@ class ShardedMatcher:
     """
 
     def __init__(self, train_shard, first_row: int, group=None, ratio=(7, 10), variant: Optional[str] = None,
-                 local_keys: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_keys: Optional[Callable] = None, merge: Optional[Callable] = None, exchange: str = "auto"):
         import torch.distributed as dist
         self.train = train_shard
         self.first_row = int(first_row)
@@ -49,6 +49,14 @@ class ShardedMatcher:
         self._merge = merge or self._cuda_merge
         self._variant = variant
         self._gather_bufs = {}
+        # exchange of the per-rank keys: "nccl" = all-gather + merge kernel; "nvlink" = one kernel that stores
+        # the keys straight into every peer's symmetric-memory buffer, flags them and merges (slm_exchange_merge);
+        # "auto" tries nvlink for small query batches and falls back to nccl when peer mapping is unavailable
+        if exchange not in ("auto", "nccl", "nvlink"):
+            raise ValueError("exchange must be auto, nccl or nvlink")
+        self.exchange = exchange if (local_keys is None and merge is None and self.world > 1) else "nccl"
+        self._symm = None
+        self._step = 0
 
     # -- CUDA implementations ---------------------------------------------------------------------
     def _ctx(self):
@@ -84,6 +92,65 @@ class ShardedMatcher:
                                           dist_.data_ptr(), acc.data_ptr(), stream))
         return idx, dist_, acc
 
+    # -- NVLink exchange ----------------------------------------------------------------------------
+    _NVLINK_MAX_NQ = 8192
+
+    def _symm_setup(self, device):
+        """Peer-mapped key buffers + flags through torch symmetric memory (NVLink / NVSwitch P2P)."""
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        cap = self._NVLINK_MAX_NQ
+        keys = symm_mem.empty((2, self.world, cap, 2), dtype=torch.int64, device=device)
+        flags = symm_mem.empty((2 * self.world,), dtype=torch.int32, device=device)
+        flags.zero_()
+        hk = symm_mem.rendezvous(keys, group)
+        hf = symm_mem.rendezvous(flags, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)                       # every rank's flags are zero before anybody publishes
+        arr = ctypes.c_uint64 * self.world
+        self._symm = dict(keys=keys, flags=flags, hk=hk, hf=hf, cap=cap, rank=dist.get_rank(group),
+                          key_ptrs=arr(*[int(x) for x in hk.buffer_ptrs]),
+                          flag_ptrs=arr(*[int(x) for x in hf.buffer_ptrs]))
+
+    def _nvlink_ready(self, q) -> bool:
+        if self.exchange == "nccl" or q.shape[0] > self._NVLINK_MAX_NQ or not getattr(q, "is_cuda", False):
+            return False
+        if self._symm is None:
+            try:
+                self._symm_setup(q.device)
+            except Exception as e:              # no peer mapping in this environment
+                if self.exchange == "nvlink":
+                    raise
+                import warnings
+                warnings.warn(f"slammatch: NVLink exchange unavailable ({e!r}); using the NCCL all-gather")
+                self.exchange = "nccl"
+                return False
+        return True
+
+    def _knn2_nvlink(self, q):
+        import ctypes
+        import torch
+        from . import _lib
+        s = self._symm
+        ctx = self._ctx()
+        nq, dev = q.shape[0], q.device
+        keys = self._cuda_local_keys(q)
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        dist_ = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        acc = torch.empty((nq,), dtype=torch.uint8, device=dev)
+        num, den = self.ratio if self.ratio is not None else (0, 1)
+        self._step += 1
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(ctx.lib.slm_exchange_merge(ctx.handle, keys.data_ptr(), nq, s["cap"],
+                                              ctypes.cast(s["key_ptrs"], ctypes.c_void_p),
+                                              ctypes.cast(s["flag_ptrs"], ctypes.c_void_p), s["rank"], self.world,
+                                              self._step, int(num), int(den), idx.data_ptr(), dist_.data_ptr(),
+                                              acc.data_ptr(), stream))
+        return idx, dist_, acc
+
     # -- the sharded query ----------------------------------------------------------------------------
     def _gather(self, keys, slot, async_op=False):
         import torch
@@ -109,6 +176,8 @@ class ShardedMatcher:
         if self.world == 1:
             keys = keys_fn(q)
             return self._merge(keys.reshape((1,) + tuple(keys.shape)))
+        if self._nvlink_ready(q):
+            return self._knn2_nvlink(q)
         if nq <= query_batch:
             if keys_fn == self._cuda_local_keys:
                 # in-place all-gather: the search writes this rank's keys straight into its slot of the buffer

@@ -17,7 +17,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, q, t, out_dir):
+def _worker(rank, world, port, q, t, out_dir, exchange="auto"):
     import torch
     import torch.distributed as dist
     from slammatch.sharded import ShardedMatcher, shard_bounds
@@ -27,10 +27,12 @@ def _worker(rank, world, port, q, t, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         a, b = shard_bounds(t.shape[0], world)[rank]
-        sm = ShardedMatcher(torch.from_numpy(t[a:b]).cuda(), a, ratio=(7, 10))
+        sm = ShardedMatcher(torch.from_numpy(t[a:b]).cuda(), a, ratio=(7, 10), exchange=exchange)
         qd = torch.from_numpy(q).cuda()
-        for _ in range(2):
+        for _ in range(5):                    # several steps: both halves of the exchange buffers get reused
             idx, dd, acc = sm.knn2(qd)
+        if rank == 0:
+            open(os.path.join(out_dir, "exchange.txt"), "w").write(sm.exchange)
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx.cpu().numpy(), dist=dd.cpu().numpy(),
                  acc=acc.cpu().numpy())
@@ -50,8 +52,10 @@ def test_nccl_sharded_query_equals_oracle(tmp_path):
     t = synth.with_duplicates(t, 18, 0.2)
     oi, od = orc.c_knn2(q, t)
     for world in sorted({2, n}):
-        mp.spawn(_worker, args=(world, _free_port(), q, t, str(tmp_path)), nprocs=world, join=True)
-        for r in range(world):
-            z = np.load(tmp_path / f"rank{r}.npz")
-            assert np.array_equal(z["idx"], oi) and np.array_equal(z["dist"], od), (world, r)
-            assert np.array_equal(z["acc"], orc.c_ratio(od, 7, 10)), (world, r)
+        for exchange in ("nccl", "auto"):
+            mp.spawn(_worker, args=(world, _free_port(), q, t, str(tmp_path), exchange), nprocs=world, join=True)
+            print("world", world, "exchange requested", exchange, "used", open(tmp_path / "exchange.txt").read())
+            for r in range(world):
+                z = np.load(tmp_path / f"rank{r}.npz")
+                assert np.array_equal(z["idx"], oi) and np.array_equal(z["dist"], od), (world, r, exchange)
+                assert np.array_equal(z["acc"], orc.c_ratio(od, 7, 10)), (world, r, exchange)
