@@ -481,7 +481,7 @@ def ours(args, w, cfg_id):
             "config": {"workload": w["name"], "nq": nq, "nt": nt, "variant": variant, "variant_requested": args.variant,
                        "l2": "inputs larger than L2 (streamed from HBM every step)" if flush is None
                              else "256 MiB L2 flush between timed steps",
-                       "parallelism": (f"train rows sharded over {world} ranks, exchange of packed top-2 keys ({sm.exchange}) + merge"
+                       "parallelism": (f"train rows sharded over {world} ranks, exchange of packed top-2 keys ({sm.last_exchange}) + merge"
                                        if sharded else ("single GPU" if world == 1 else f"{world} replicas"))},
             "matched_queries_per_s": matched * jobs / (dev_ms / args.steps * 1e-3),
             "matched_per_step": matched,

@@ -57,6 +57,7 @@ class ShardedMatcher:
         self.exchange = exchange if (local_keys is None and merge is None and self.world > 1) else "nccl"
         self._symm = None
         self._step = 0
+        self.last_exchange = "none"     # what the last knn2() call actually used
 
     # -- CUDA implementations ---------------------------------------------------------------------
     def _ctx(self):
@@ -177,7 +178,9 @@ class ShardedMatcher:
             keys = keys_fn(q)
             return self._merge(keys.reshape((1,) + tuple(keys.shape)))
         if self._nvlink_ready(q):
+            self.last_exchange = "nvlink peer stores + flags (slm_exchange_merge)"
             return self._knn2_nvlink(q)
+        self.last_exchange = "nccl all-gather"
         if nq <= query_batch:
             if keys_fn == self._cuda_local_keys:
                 # in-place all-gather: the search writes this rank's keys straight into its slot of the buffer

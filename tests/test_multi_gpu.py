@@ -32,7 +32,7 @@ def _worker(rank, world, port, q, t, out_dir, exchange="auto"):
         for _ in range(5):                    # several steps: both halves of the exchange buffers get reused
             idx, dd, acc = sm.knn2(qd)
         if rank == 0:
-            open(os.path.join(out_dir, "exchange.txt"), "w").write(sm.exchange)
+            open(os.path.join(out_dir, "exchange.txt"), "w").write(sm.last_exchange)
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx.cpu().numpy(), dist=dd.cpu().numpy(),
                  acc=acc.cpu().numpy())
