@@ -152,6 +152,18 @@ int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys_dev, int64_t nq,
                        int32_t *dist_out_dev, uint8_t *accept_out_dev, void *stream);
 
 /*
+ * The whole sharded step in one call: search this rank's train block, exchange over NVLink, merge, finalise.
+ * Arguments as slm_knn2_keys + slm_exchange_merge.  With the tensor variant the refine kernel stores each query's
+ * keys straight into the peers' buffers and its last block publishes the flags, waits and merges -- no
+ * separate exchange kernel; other variants run the search followed by slm_exchange_merge.
+ */
+int slm_knn2_exchange(slm_ctx *ctx, const uint32_t *q_dev, int64_t nq, const uint32_t *t_dev, int64_t nt,
+                      int64_t train_index_base, int64_t nq_capacity, const uint64_t *peer_keys_host,
+                      const uint64_t *peer_flags_host, int32_t rank, int32_t world, uint32_t step, int32_t ratio_num,
+                      int32_t ratio_den, int32_t *idx_out_dev, int32_t *dist_out_dev, uint8_t *accept_out_dev,
+                      void *stream);
+
+/*
  * Device-side compaction of accepted rows (the gathers at tracking.py:32-33 start from this list):
  * writes (queryIdx, trainIdx, distance) int32 triples in ascending queryIdx order to matches_out_dev
  * (capacity nq triples) and the count to count_out_dev (int32[1]).

@@ -181,6 +181,7 @@ int slm_destroy(slm_ctx *ctx)
     for (slm_buf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->done_counter) cudaFree(ctx->done_counter);
     if (ctx->prof_ev) {
         for (int i = 0; i < slm_ctx::kMaxProf; ++i) cudaEventDestroy(ctx->prof_ev[i]);
         delete[] ctx->prof_ev;
@@ -345,6 +346,48 @@ int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys, int64_t nq, int
     SLM_TRY(slm_exchange_merge_impl(ctx, local_keys, nq, nq_capacity, peer_keys_host, peer_flags_host, rank, world, step,
                                     ratio_num, ratio_den, idx_out, dist_out, accept_out, (cudaStream_t)stream));
     return slm_prof_mark(ctx, (cudaStream_t)stream, SLM_TAG_CALL_END);
+}
+
+int slm_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                      int64_t nq_capacity, const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank,
+                      int32_t world, uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out,
+                      int32_t *dist_out, uint8_t *accept_out, void *stream_)
+{
+    SLM_TRY(check_ctx(ctx));
+    SLM_TRY(check_sizes(nq, nt, base));
+    if (world < 1 || world > kSlmMaxWorld || rank < 0 || rank >= world)
+        return slm_fail(SLM_ERR_INVALID, "bad rank/world (%d/%d)", rank, world);
+    if (nq < 1 || nq > 8192 || nq > nq_capacity) return slm_fail(SLM_ERR_INVALID, "nq must be in 1..min(8192, nq_capacity)");
+    if (step == 0) return slm_fail(SLM_ERR_INVALID, "step starts at 1");
+    if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
+    if (!q || (nt > 0 && !t) || !peer_keys_host || !peer_flags_host) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool tensor = nt > 0 && (ctx->variant == SLM_VARIANT_TENSOR ||
+                                   (ctx->variant == SLM_VARIANT_AUTO && nq > 8 && nq * nt >= (1ll << 18)));
+    SLM_TRY(slm_prof_mark(ctx, stream, SLM_TAG_CALL_BEGIN));
+    if (tensor) {
+        if (!ctx->done_counter) {
+            SLM_CUDA(cudaMalloc(&ctx->done_counter, sizeof(unsigned)));
+            SLM_CUDA(cudaMemset(ctx->done_counter, 0, sizeof(unsigned)));
+        }
+        slm_exchange ex{};
+        for (int r = 0; r < world; ++r) {
+            ex.peer_keys[r] = reinterpret_cast<unsigned long long *>(peer_keys_host[r]);
+            ex.peer_flags[r] = reinterpret_cast<unsigned *>(peer_flags_host[r]);
+        }
+        ex.rank = rank; ex.world = world; ex.step = step; ex.cap = nq_capacity;
+        ex.ratio_num = ratio_num; ex.ratio_den = ratio_den;
+        ex.idx_out = idx_out; ex.dist_out = dist_out; ex.accept_out = accept_out;
+        ex.done_counter = ctx->done_counter;
+        SLM_TRY(slm_tc_knn2_exchange(ctx, q, nq, t, nt, base, ex, stream));
+    } else {
+        SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)nq * 16));
+        uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
+        SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys, stream));
+        SLM_TRY(slm_exchange_merge_impl(ctx, keys, nq, nq_capacity, peer_keys_host, peer_flags_host, rank, world, step,
+                                        ratio_num, ratio_den, idx_out, dist_out, accept_out, stream));
+    }
+    return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
 }
 
 int slm_compact_matches(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,

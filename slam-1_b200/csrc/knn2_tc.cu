@@ -550,7 +550,8 @@ __device__ __forceinline__ void top2_insert_max(unsigned long long &k1, unsigned
 //            the reference tie-break.  Keys are (distance << 6 | position), position = 0..31 in the
 //            lower-index chunk, 32..63 in the higher one, so 32-bit min == (distance, global index) order.
 template <int G>
-__global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long base, unsigned long long *keys_out)
+__global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long base, unsigned long long *keys_out,
+                                                        slm_exchange ex)
 {
     constexpr int kQPW = 32 / G;   // queries per warp
     const int lane = threadIdx.x & 31, sub = lane % G;
@@ -637,7 +638,59 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
             const long long row = (long long)(pos < 32 ? glo : ghi) * kChunk + (pos & 31u);
             return ((unsigned long long)(k >> 6) << 32) | (unsigned long long)(base + row);
         };
-        reinterpret_cast<ulonglong2 *>(keys_out)[gq] = make_ulonglong2(widen(k1), widen(k2));
+        const ulonglong2 kk = make_ulonglong2(widen(k1), widen(k2));
+        if (keys_out) reinterpret_cast<ulonglong2 *>(keys_out)[gq] = kk;
+        if (ex.world > 0) {
+            // sharded path: this query's keys go straight into slot [step & 1][rank] of every peer's buffer
+            const long long slot = ((long long)(ex.step & 1u) * ex.world + ex.rank) * ex.cap + gq;
+            for (int r = 0; r < ex.world; ++r) reinterpret_cast<ulonglong2 *>(ex.peer_keys[r])[slot] = kk;
+        }
+    }
+    if (ex.world > 0) {
+        // last-block-done: the block that finishes last publishes this rank's flags, waits (bounded) for every
+        // peer's keys of this step and merges + finalises all queries from the local buffer
+        __shared__ bool is_last;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(ex.done_counter, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!is_last) return;
+        const unsigned parity = ex.step & 1u;
+        if (threadIdx.x == 0) *ex.done_counter = 0;
+        if ((int)threadIdx.x < ex.world) {
+            __threadfence_system();
+            unsigned *flag = ex.peer_flags[threadIdx.x] + parity * ex.world + ex.rank;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(ex.step) : "memory");
+            const unsigned *mine = ex.peer_flags[ex.rank] + parity * ex.world + threadIdx.x;
+            unsigned v, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+                if (++spins > (1u << 27)) {
+                    printf("slammatch: exchange flag of rank %d never reached step %u (have %u)\n", (int)threadIdx.x,
+                           ex.step, v);
+                    __trap();
+                }
+            } while ((int)(v - ex.step) < 0);
+        }
+        __syncthreads();
+        const unsigned long long *g = ex.peer_keys[ex.rank] + (long long)parity * ex.world * ex.cap * 2;
+        const long long n_q = (long long)p.n_prob * p.nq;
+        for (long long i = threadIdx.x; i < n_q; i += blockDim.x) {
+            unsigned long long m1 = kKeyNone, m2 = kKeyNone;
+            for (int r = 0; r < ex.world; ++r) {
+                const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(g)[(long long)r * ex.cap + i];
+                top2_insert(m1, m2, v.x);
+                top2_insert(m1, m2, v.y);
+            }
+            const bool has1 = m1 != kKeyNone, has2 = m2 != kKeyNone;
+            const int i1 = has1 ? (int)(m1 & 0xFFFFFFFFull) : -1, d1 = has1 ? (int)(m1 >> 32) : -1;
+            const int i2 = has2 ? (int)(m2 & 0xFFFFFFFFull) : -1, d2 = has2 ? (int)(m2 >> 32) : -1;
+            if (ex.idx_out) reinterpret_cast<int2 *>(ex.idx_out)[i] = make_int2(i1, i2);
+            if (ex.dist_out) reinterpret_cast<int2 *>(ex.dist_out)[i] = make_int2(d1, d2);
+            if (ex.accept_out)
+                ex.accept_out[i] = (ex.ratio_num > 0 ? (has1 && has2 && (long long)ex.ratio_den * d1 < (long long)ex.ratio_num * d2)
+                                                     : has1) ? 1 : 0;
+        }
     }
 }
 
@@ -676,7 +729,8 @@ int launch_tc2(const TcParams &p, int n_prob, cudaStream_t stream)
     return SLM_OK;
 }
 
-int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_out, cudaStream_t stream)
+int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_out, cudaStream_t stream,
+           const slm_exchange *exchange = nullptr)
 {
     ctx->last_variant = SLM_VARIANT_TENSOR;
     p.n_prob = n_prob;
@@ -768,12 +822,14 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     }
     SLM_TRY(slm_prof_end(ctx, stream));
     const long long n_q = (long long)n_prob * p.nq;
+    slm_exchange ex{};
+    if (exchange) ex = *exchange;
     if (p.cpg * p.n_epochs * 4 <= 32) {   // few candidates per query (many queries, short train sets): 8 lanes each
         tc_refine_kernel<8><<<(unsigned)((n_q + 31) / 32), 256, 0, stream>>>(
-            p, base, reinterpret_cast<unsigned long long *>(keys_out));
+            p, base, reinterpret_cast<unsigned long long *>(keys_out), ex);
     } else {                          // many ranges (long train sets): a full warp per query
         tc_refine_kernel<32><<<(unsigned)((n_q + 7) / 8), 256, 0, stream>>>(
-            p, base, reinterpret_cast<unsigned long long *>(keys_out));
+            p, base, reinterpret_cast<unsigned long long *>(keys_out), ex);
     }
     SLM_CUDA(cudaGetLastError());
     ctx->launches += 2;
@@ -789,6 +845,15 @@ int slm_tc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t
     p.q = q; p.t = t; p.desc = nullptr; p.pairs = nullptr; p.frame_words = 0;
     p.nq = (int)nq; p.nt = (int)nt;
     return tc_run(ctx, p, 1, base, keys_out, stream);
+}
+
+int slm_tc_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                         const slm_exchange &ex, cudaStream_t stream)
+{
+    TcParams p{};
+    p.q = q; p.t = t; p.desc = nullptr; p.pairs = nullptr; p.frame_words = 0;
+    p.nq = (int)nq; p.nt = (int)nt;
+    return tc_run(ctx, p, 1, base, nullptr, stream, &ex);
 }
 
 int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,

@@ -39,6 +39,7 @@ struct slm_ctx {
     cudaEvent_t chunk_ev[kMaxHostChunks] = {};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // optional timing of the dominant kernel (slm_profile_enable)
+    unsigned *done_counter = nullptr;   // 4-byte device counter (slm_tc_knn2_exchange)
     int profile = 0;
     static constexpr int kMaxProf = 4096;
     cudaEvent_t *prof_ev = nullptr;   // kMaxProf events, created lazily
@@ -114,9 +115,29 @@ int slm_exchange_merge_impl(slm_ctx *ctx, const uint64_t *local_keys, int64_t nq
 int slm_compact(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
                 int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, cudaStream_t stream);
 
+// ---- NVLink exchange of per-rank keys (sharded path) ---------------------------------------------------
+// Every rank's key buffer uint64[2][world][cap][2] and flag array uint32[2][world] are peer-mapped on this GPU.
+static constexpr int kSlmMaxWorld = 16;
+struct slm_exchange {
+    unsigned long long *peer_keys[kSlmMaxWorld];
+    unsigned *peer_flags[kSlmMaxWorld];
+    int rank, world;
+    unsigned step;
+    long long cap;
+    // outputs of the fused merge + finalize
+    int ratio_num, ratio_den;
+    int *idx_out, *dist_out;
+    unsigned char *accept_out;
+    unsigned *done_counter;   // device counter for the last-block-done pattern (zero between launches)
+};
+
 // ---- variant T: +-1 fp8 expansion + tcgen05.mma with TMEM accumulators (knn2_tc.cu) ---------------
 int slm_tc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
                      int64_t base, uint64_t *keys_out, cudaStream_t stream);
+// Search + NVLink exchange + merge + finalize: the refine kernel stores each query's keys straight into every
+// peer's buffer; its last block publishes the flags, waits for the peers and merges (no separate kernel).
+int slm_tc_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                         const slm_exchange &ex, cudaStream_t stream);
 int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
                              int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream);
 

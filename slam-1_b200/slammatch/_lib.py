@@ -21,7 +21,7 @@ SYMBOLS = (
     "slm_launch_count",
     "slm_profile_enable", "slm_profile_read",
     "slm_knn2", "slm_knn2_keys", "slm_knn2_filter", "slm_knn2_batched", "slm_merge_top2",
-    "slm_exchange_merge",
+    "slm_exchange_merge", "slm_knn2_exchange",
     "slm_compact_matches", "slm_gather_rows", "slm_bow_hist", "slm_chi2_scan",
     "slm_knn2_host",
 )
@@ -70,6 +70,8 @@ def load():
         lib.slm_knn2_batched.argtypes = [vp, vp, i64, i64, vp, i64, i32, i32, vp, vp, vp, vp]
         lib.slm_merge_top2.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, vp]
         lib.slm_exchange_merge.argtypes = [vp, vp, i64, i64, vp, vp, i32, i32, ctypes.c_uint32, i32, i32, vp, vp, vp, vp]
+        lib.slm_knn2_exchange.argtypes = [vp, vp, i64, vp, i64, i64, i64, vp, vp, i32, i32, ctypes.c_uint32, i32, i32,
+                                          vp, vp, vp, vp]
         lib.slm_compact_matches.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
         lib.slm_gather_rows.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp, vp]
         lib.slm_bow_hist.argtypes = [vp, vp, i64, i32, i32, vp, vp]

@@ -117,7 +117,7 @@ class ShardedMatcher:
                           flag_ptrs=arr(*[int(x) for x in hf.buffer_ptrs]))
 
     def _nvlink_ready(self, q) -> bool:
-        if self.exchange == "nccl" or q.shape[0] > self._NVLINK_MAX_NQ or not getattr(q, "is_cuda", False):
+        if self.exchange == "nccl" or not (0 < q.shape[0] <= self._NVLINK_MAX_NQ) or not getattr(q, "is_cuda", False):
             return False
         if self._symm is None:
             try:
@@ -138,18 +138,18 @@ class ShardedMatcher:
         s = self._symm
         ctx = self._ctx()
         nq, dev = q.shape[0], q.device
-        keys = self._cuda_local_keys(q)
         idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
         dist_ = torch.empty((nq, 2), dtype=torch.int32, device=dev)
         acc = torch.empty((nq,), dtype=torch.uint8, device=dev)
         num, den = self.ratio if self.ratio is not None else (0, 1)
         self._step += 1
+        nt = self.train.shape[0]
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(ctx.lib.slm_exchange_merge(ctx.handle, keys.data_ptr(), nq, s["cap"],
-                                              ctypes.cast(s["key_ptrs"], ctypes.c_void_p),
-                                              ctypes.cast(s["flag_ptrs"], ctypes.c_void_p), s["rank"], self.world,
-                                              self._step, int(num), int(den), idx.data_ptr(), dist_.data_ptr(),
-                                              acc.data_ptr(), stream))
+        _lib.check(ctx.lib.slm_knn2_exchange(ctx.handle, q.data_ptr(), nq, self.train.data_ptr() if nt else None, nt,
+                                             self.first_row, s["cap"], ctypes.cast(s["key_ptrs"], ctypes.c_void_p),
+                                             ctypes.cast(s["flag_ptrs"], ctypes.c_void_p), s["rank"], self.world,
+                                             self._step, int(num), int(den), idx.data_ptr(), dist_.data_ptr(),
+                                             acc.data_ptr(), stream))
         return idx, dist_, acc
 
     # -- the sharded query ----------------------------------------------------------------------------
