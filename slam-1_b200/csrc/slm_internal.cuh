@@ -74,15 +74,6 @@ int slm_fail(int code, const char *fmt, ...);
 // earlier calls that still use it have finished).
 int slm_buf_reserve(slm_ctx *ctx, slm_buf *buf, size_t bytes);
 
-// One problem = one (query set, train set) pair.  Batched calls pass several via device memory.
-struct slm_problem {
-    const uint32_t *q;   // uint32[nq][8]
-    const uint32_t *t;   // uint32[nt][8]
-    int nq;
-    int nt;
-    long long base;      // global index of train row 0
-};
-
 // ---- variant P: LOP3(XOR)+POPC on the integer pipe (knn2_popc.cu) --------------------------------
 // Single problem or a batch of equally-shaped problems (n_prob >= 1, pairs given by frame indices).
 // Writes packed keys uint64[n_prob][nq][2].

@@ -124,7 +124,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
-// Same load without the wait (software pipelining); pair with tmem_ld_wait() + keep_alive().
+// Same load without the wait (several loads in flight); pair with tmem_ld_wait() / pin_regs().
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
