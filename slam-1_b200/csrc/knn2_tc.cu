@@ -479,7 +479,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
                     load_row(r2, bt2, et, n0, n1);
                     if (two_rows) load_row(r2, bt2, et + kExp2Threads, m0, m1);
                 }
-                tc::mbar_wait(&bars->b_empty[s], ph ^ 1, 20 + s);
+                tc::mbar_wait_backoff(&bars->b_empty[s], ph ^ 1, 20 + s, 200);
                 tc::expand_row_to_smem(sB_addr + (uint32_t)s * kBHalfBytes, et, c0, c1);
                 if (two_rows) tc::expand_row_to_smem(sB_addr + (uint32_t)s * kBHalfBytes, et + kExp2Threads, e0, e1);
                 tc::fence_proxy_async();

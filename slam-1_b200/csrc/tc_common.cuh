@@ -56,6 +56,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int ta
         }
     }
 }
+// Same, for waiters that are far ahead of their producer (expanders three stages ahead of the MMA): back off
+// between polls so the spinning warp does not burn issue slots and power -- the kernel runs power-limited
+// (GPC clock 1.75 GHz under load), so idle polling costs clock.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, int tag, unsigned ns)
+{
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (++spins > (1u << 24)) {
+            printf("slammatch: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
+                   threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
