@@ -394,6 +394,7 @@ def ours(args, w, cfg_id):
         except Exception:
             pass
         variant = ctx.last_variant()
+        kernel_name = ctx.last_kernel()
         per_rank_cmp = cmp_per_step / (world if sharded else 1)
         kern_avg_ms = kern_ms / max(kern_n, 1)
         kernels_per_step = max(kern_n // (args.steps + 1), 1)   # the profile also holds the ramp step
@@ -418,13 +419,13 @@ def ours(args, w, cfg_id):
             peak = max(2.0 * bf16, macs * 2.0 * sms * clk_mhz * 1e6 / 1e12)
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": (ach / peak) if ach else None, "traffic": None,
-                    "kernel": "knn2_tc_kernel", "kernel_ms": kern_avg_ms,
+                    "kernel": kernel_name or "knn2_tc2_kernel", "kernel_ms": kern_avg_ms,
                     "peak_note": ("max(2 x measured cuBLAS bf16 burst %.1f TF/s [%s], tcgen05 kind::f8f6f4 ceiling = %d MAC/clk/SM "
                                   "(own probe) x 2 x %d SMs x %.0f MHz max SM clock)"
                                   % (bf16, "MEASURED_PEAKS.json" if peaks else "fallback", macs, sms, clk_mhz)),
                     "frac_vs_2x_bf16_measured": (ach / (2.0 * bf16)) if ach else None,
                     "algorithmic_unit": "1 cmp = 512 fp8 flop (256-bit +-1 dot product)"}
-        elif nq <= 8 and variant == "popc" and args.variant == "auto":
+        elif kernel_name == "knn2_stream_kernel":
             # nq <= 8 runs knn2_stream_kernel: the train set streams through the SMs once
             alg_bytes = 32.0 * (nq + nt / (world if sharded else 1)) + 16.0 * nq
             ach = alg_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else None
@@ -452,7 +453,7 @@ def ours(args, w, cfg_id):
             ach = cmp_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
             peak = popc_rate / 8 / 1e12
             roof = {"bound": "int_popc(xu pipe)", "achieved": ach, "peak": peak, "unit": "Tcmp/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None, "kernel": "knn2_popc_kernel",
+                    "frac": (ach / peak) if ach else None, "traffic": None, "kernel": kernel_name or "knn2_popc_kernel",
                     "kernel_ms": kern_avg_ms,
                     "peak_note": "measured POPC32 lanes/clk/SM (own probe) x SMs x max SM clock / 8 POPC per cmp"}
         tr = os.path.join(ROOT, "profiles", "traffic.json")

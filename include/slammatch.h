@@ -85,6 +85,9 @@ int slm_destroy(slm_ctx *ctx);
 int slm_set_variant(slm_ctx *ctx, int variant);
 /* The variant the last search on this ctx actually ran (resolves SLM_VARIANT_AUTO); 0 before any search. */
 int slm_last_variant(const slm_ctx *ctx);
+/* Name of the distance kernel the last search on this ctx launched ("knn2_tc2_kernel", "knn2_frame_kernel", ...);
+ * "" before any search.  The string is static. */
+const char *slm_last_kernel(const slm_ctx *ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches evidence). */
 int64_t slm_launch_count(const slm_ctx *ctx);
 /*
@@ -196,6 +199,20 @@ int slm_bow_hist(slm_ctx *ctx, const int32_t *words_dev, int64_t n, int32_t stri
                  int32_t *hist_out_dev, void *stream);
 int slm_chi2_scan(slm_ctx *ctx, const int32_t *hist_dev, const int32_t *db_dev, int64_t n_db, int32_t n_words,
                   double *dist_out_dev, int32_t *best_idx_dev, double *best_val_dev, void *stream);
+
+/*
+ * Binary vocabulary training, one update step (bag_of_words.py:14,20 `KMeans.fit`, re-specified in Hamming space as
+ * k-majority).  The assignment step is the search itself (word = idx[:,0] of
+ * slm_knn2 against the current vocabulary); this call then rewrites every word of vocab_dev uint32[n_words][8]
+ * IN PLACE as the bitwise majority of the descriptors assigned to it: bit <- 1 if more than half of the members
+ * have it set, unchanged on an exact tie; words without members keep their centroid.
+ *   desc_dev  uint32[n][8]; words_dev holds one word id every `stride` int32 (ids outside [0, n_words) are skipped)
+ *   counts_out_dev   int32[n_words] members per word (optional)
+ *   changed_out_dev  int32[1] number of words whose centroid changed (optional; 0 = converged)
+ */
+int slm_vocab_update(slm_ctx *ctx, const uint32_t *desc_dev, int64_t n, const int32_t *words_dev, int32_t stride,
+                     uint32_t *vocab_dev, int32_t n_words, int32_t *counts_out_dev, int32_t *changed_out_dev,
+                     void *stream);
 
 /*
  * Host-memory convenience: what the Python shim's knnMatch(des1, des2, k=2) calls.  q_host/t_host are

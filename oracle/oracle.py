@@ -336,3 +336,57 @@ def np_predict_previous(h, db, img_index: int, threshold: int):
     for i in range(0, (img_index + 1 - threshold)):
         dist.append(np_chi2(h, db[i]))
     return np.argmin(dist), np.min(dist)
+
+
+# ----------------------------------------------------------------------------------------------
+# Binary vocabulary training (bag_of_words.py:14,20 KMeans.fit, re-specified as k-majority in Hamming
+# space: SURVEY.md section 8(f) rank 3).  No reference arithmetic exists for this (the reference clusters
+# float vectors with sklearn and cannot be constructed on a current sklearn): the rule
+# below IS the specification the CUDA path (csrc/vocab.cu) is held to -- parity unpinned for this row.
+# ----------------------------------------------------------------------------------------------
+def np_vocab_update(desc, words, vocab):
+    """One update step: every word becomes the bitwise majority of its members; an exact tie keeps the old
+    bit, a word without members keeps its centroid.  Returns (new vocab uint8[k,32], members int32[k], changed)."""
+    desc, vocab = _as_desc(desc), _as_desc(vocab).copy()
+    words = np.asarray(words)
+    k = vocab.shape[0]
+    counts = np.zeros(k, dtype=np.int32)
+    changed = 0
+    for w in range(k):
+        rows = desc[words == w]
+        m = rows.shape[0]
+        counts[w] = m
+        if m == 0:
+            continue
+        ones = np.unpackbits(rows, axis=1, bitorder="little").astype(np.int64).sum(axis=0)
+        old = np.unpackbits(vocab[w], bitorder="little")
+        new = np.where(2 * ones > m, 1, np.where(2 * ones == m, old, 0)).astype(np.uint8)
+        packed = np.packbits(new, bitorder="little")
+        if not np.array_equal(packed, vocab[w]):
+            changed += 1
+            vocab[w] = packed
+    return vocab, counts, changed
+
+
+def vocab_init(desc, k: int, seed: int):
+    """Initial vocabulary: k distinct rows of the pool, chosen by a seeded numpy Generator (shared by the CUDA
+    path's host side and by this restatement, so that both start from the same words)."""
+    desc = _as_desc(desc)
+    if not 1 <= k <= desc.shape[0]:
+        raise ValueError("need 1 <= k <= number of descriptors")
+    rows = np.random.default_rng(seed).choice(desc.shape[0], size=k, replace=False)
+    return desc[np.sort(rows)].copy()
+
+
+def np_train_vocabulary(desc, k: int, iters: int = 10, seed: int = 0, knn=None):
+    """Lloyd iterations in Hamming space: assign (nearest word, lowest index on ties) + np_vocab_update, until no
+    centroid changes or `iters` is reached.  Returns (vocab, iterations run)."""
+    knn = knn or np_knn2
+    vocab = vocab_init(desc, k, seed)
+    it = 0
+    for it in range(1, iters + 1):
+        words = knn(desc, vocab)[0][:, 0]
+        vocab, _, changed = np_vocab_update(desc, words, vocab)
+        if changed == 0:
+            break
+    return vocab, it

@@ -161,6 +161,11 @@ int slm_create(int device, slm_ctx **ctx_out)
         int v = atoi(e);
         if (v >= 1) ctx->max_cpg = v;
     }
+    if (const char *e = getenv("SLM_FRAME_MAX_CLK")) ctx->frame_max_clk = atoll(e);
+    if (const char *e = getenv("SLM_FRAME_WARPS")) {
+        int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16) ctx->frame_warps = v;
+    }
     if (const char *e = getenv("SLM_TC_EPOCH_TILES")) {
         int v = atoi(e);
         if (v >= 8 && v <= 4096) ctx->epoch_tiles = v;
@@ -177,7 +182,7 @@ int slm_destroy(slm_ctx *ctx)
     if (!ctx) return SLM_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    slm_buf *bufs[] = {&ctx->scratch, &ctx->keys, &ctx->rev, &ctx->misc, &ctx->io};
+    slm_buf *bufs[] = {&ctx->scratch, &ctx->keys, &ctx->rev, &ctx->misc, &ctx->io, &ctx->tickets};
     for (slm_buf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
@@ -209,6 +214,7 @@ int slm_set_variant(slm_ctx *ctx, int variant)
 
 int64_t slm_launch_count(const slm_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int slm_last_variant(const slm_ctx *ctx) { return ctx ? ctx->last_variant : 0; }
+const char *slm_last_kernel(const slm_ctx *ctx) { return ctx ? ctx->last_kernel : ""; }
 
 int slm_profile_enable(slm_ctx *ctx, int enable)
 {
@@ -265,12 +271,22 @@ int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t 
     if (nq == 0) return SLM_OK;
     if (!q || (nt > 0 && !t)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
     cudaStream_t stream = (cudaStream_t)stream_;
+    const bool cross = cross_check && accept_out && nt > 0;
+    if (ctx->variant == SLM_VARIANT_AUTO && nt > 0 && slm_frame_eligible(ctx, nq, nt, cross)) {
+        // frame-to-frame shapes: search, merge, ratio and cross-check in one launch
+        if (((uintptr_t)q & 15) || ((uintptr_t)t & 15))
+            return slm_fail(SLM_ERR_INVALID, "descriptor pointers must be 16-byte aligned");
+        SLM_TRY(slm_prof_mark(ctx, stream, SLM_TAG_CALL_BEGIN));
+        SLM_TRY(slm_frame_knn2(ctx, q, nq, t, nt, base, ratio_num, ratio_den, cross ? 1 : 0, nullptr, idx_out, dist_out,
+                               accept_out, stream));
+        return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
+    }
     SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)nq * 16));
     uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
     SLM_TRY(slm_prof_mark(ctx, stream, SLM_TAG_CALL_BEGIN));
     SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys, stream));
     const uint64_t *rev = nullptr;
-    if (cross_check && accept_out && nt > 0) {
+    if (cross) {
         // reverse search: every train row against all queries (lowest query index wins ties)
         SLM_TRY(slm_buf_reserve(ctx, &ctx->rev, (size_t)nt * 16));
         SLM_TRY(knn2_keys_dispatch(ctx, t, nt, q, nq, 0, reinterpret_cast<uint64_t *>(ctx->rev.p), stream));
@@ -433,6 +449,16 @@ int slm_chi2_scan(slm_ctx *ctx, const int32_t *hist, const int32_t *db, int64_t 
     return slm_chi2_scan_impl(ctx, hist, db, n_db, n_words, dist_out, best_idx, best_val, (cudaStream_t)stream);
 }
 
+int slm_vocab_update(slm_ctx *ctx, const uint32_t *desc, int64_t n, const int32_t *words, int32_t stride, uint32_t *vocab,
+                     int32_t n_words, int32_t *counts_out, int32_t *changed_out, void *stream)
+{
+    SLM_TRY(check_ctx(ctx));
+    if (n < 0 || n > 0x7FFFFFFFll || stride < 1 || n_words < 1)
+        return slm_fail(SLM_ERR_INVALID, "bad size (n=%lld stride=%d n_words=%d)", (long long)n, stride, n_words);
+    if (!vocab || (n > 0 && (!desc || !words))) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    return slm_vocab_update_impl(ctx, desc, n, words, stride, vocab, n_words, counts_out, changed_out, (cudaStream_t)stream);
+}
+
 int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t *t_host, int64_t nt,
                   int32_t ratio_num, int32_t ratio_den, int32_t cross_check, int32_t *idx_out,
                   int32_t *dist_out, uint8_t *accept_out)
@@ -485,9 +511,14 @@ int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t
         SLM_TRY(slm_knn2_filter(ctx, q_dev, nq, t_dev, nt, 0, ratio_num, ratio_den, cross_check, idx_dev, dist_dev,
                                 accept_out ? acc_dev : nullptr, s));
     }
-    if (idx_out) SLM_CUDA(cudaMemcpyAsync(pin, idx_dev, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
-    if (dist_out) SLM_CUDA(cudaMemcpyAsync(pin + i_b, dist_dev, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
-    if (accept_out) SLM_CUDA(cudaMemcpyAsync(pin + 2 * i_b, acc_dev, (size_t)nq, cudaMemcpyDeviceToHost, s));
+    if (idx_out && dist_out && accept_out && 2 * i_b + a_b <= (1u << 20)) {
+        // small results: [idx | dist | accept] are contiguous on the device, one copy instead of three
+        SLM_CUDA(cudaMemcpyAsync(pin, idx_dev, 2 * i_b + (size_t)nq, cudaMemcpyDeviceToHost, s));
+    } else {
+        if (idx_out) SLM_CUDA(cudaMemcpyAsync(pin, idx_dev, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+        if (dist_out) SLM_CUDA(cudaMemcpyAsync(pin + i_b, dist_dev, (size_t)nq * 8, cudaMemcpyDeviceToHost, s));
+        if (accept_out) SLM_CUDA(cudaMemcpyAsync(pin + 2 * i_b, acc_dev, (size_t)nq, cudaMemcpyDeviceToHost, s));
+    }
     SLM_CUDA(cudaStreamSynchronize(s));
     if (idx_out) memcpy(idx_out, pin, (size_t)nq * 8);
     if (dist_out) memcpy(dist_out, pin + i_b, (size_t)nq * 8);

@@ -9,6 +9,9 @@ int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
     // The tensor-pipe variant is ~9x faster at scale; the integer-pipe variant has the smaller
     // fixed cost, which wins only for tiny problems.
     // a handful of queries against a long train set is HBM-bound: stream the train rows once
+    // frame-to-frame shapes: one launch instead of three
+    if (slm_frame_eligible(ctx, nq, nt, false))
+        return slm_frame_knn2(ctx, q, nq, t, nt, base, 0, 1, 0, keys_out, nullptr, nullptr, nullptr, stream);
     if (nq <= 8) return slm_stream_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
     if (nq * nt < kAutoTensorMinCmp) return slm_popc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
     return slm_tc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);

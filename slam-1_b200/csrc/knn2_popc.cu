@@ -286,6 +286,7 @@ int popc_launch(slm_ctx *ctx, PopcParams p, int n_prob, long long base, uint64_t
                 bool bmma = false)
 {
     ctx->last_variant = bmma ? SLM_VARIANT_BMMA : SLM_VARIANT_POPC;
+    ctx->last_kernel = bmma ? "knn2_bmma_kernel" : "knn2_popc_kernel";
     const int per_cta = bmma ? kBmmaQueriesPerCta : kQueriesPerCta;
     const int qblocks = (p.nq + per_cta - 1) / per_cta;
     // enough CTAs for ~8 resident per SM; never split below one tile; local index must fit kIdxBits

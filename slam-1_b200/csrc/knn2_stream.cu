@@ -104,6 +104,7 @@ int slm_stream_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint
                          uint64_t *keys_out, cudaStream_t stream)
 {
     ctx->last_variant = SLM_VARIANT_POPC;
+    ctx->last_kernel = "knn2_stream_kernel";
     if (nq < 1 || nq > 8) return slm_fail(SLM_ERR_INVALID, "stream kernel handles 1..8 queries");
     long long ctas = (nt + (long long)kStreamThreads * kRowsInFlight - 1) / ((long long)kStreamThreads * kRowsInFlight);
     const long long max_ctas = (long long)ctx->sm_count * 8;

@@ -805,6 +805,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     SLM_TRY(slm_buf_reserve(ctx, &ctx->scratch, cand_bytes));
     p.cand = reinterpret_cast<float2 *>(ctx->scratch.p);
 
+    ctx->last_kernel = two_cta ? "knn2_tc2_kernel" : "knn2_tc_kernel";
     SLM_TRY(slm_prof_begin(ctx, stream));
     if (two_cta) {
         switch (p.mt) {

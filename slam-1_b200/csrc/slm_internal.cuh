@@ -21,9 +21,13 @@ struct slm_ctx {
     int sm_count = 148;
     int variant = SLM_VARIANT_AUTO;
     int last_variant = 0;
+    const char *last_kernel = "";   // name of the distance kernel the last search launched (slm_last_kernel)
     int epoch_tiles = 4096;   // tiles per candidate epoch (SLM_TC_EPOCH_TILES shrinks it so tests reach the epoch logic)
     int max_cpg = 1 << 30;    // cap on clusters per query-group pair (SLM_TC_MAX_CPG, tests only)
     int force_1cta = 0;   // debugging / A-B: run the single-CTA tcgen05 kernel even when CTA pairs apply
+    int frame_warps = 8;               // warps per CTA of the frame kernel: 4, 8 or 16 (SLM_FRAME_WARPS)
+    long long frame_max_clk = 26000;   // AUTO prefers the single-launch frame kernel up to this estimated cost, twice that with
+                                       // cross-check (SLM_FRAME_MAX_CLK; 0 = never; calibration in profiles/r1_calib_frame.txt)
     int64_t launches = 0;
     // device buffers owned by the ctx, each grown on demand (never shrunk)
     slm_buf scratch;   // variant-internal partial results
@@ -31,6 +35,7 @@ struct slm_ctx {
     slm_buf rev;       // reverse-search packed keys (cross-check)
     slm_buf misc;      // pair lists, expanded operands, ...
     slm_buf io;        // device copies of host inputs / outputs (slm_knn2_host)
+    slm_buf tickets;   // per-group atomic tickets of the frame kernel (zero between launches)
     // pinned staging for host results
     void *pin = nullptr;
     size_t pin_bytes = 0;
@@ -86,6 +91,13 @@ int slm_popc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per
 // ---- streaming kernel for nq <= 8 (HBM-bound shapes; knn2_stream.cu) -------------------------------------
 int slm_stream_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
                          int64_t base, uint64_t *keys_out, cudaStream_t stream);
+
+// ---- frame-to-frame shapes in one launch: search + merge + ratio (+ cross-check) (knn2_frame.cu) ------------
+// keys_out (uint64[nq][2]) and idx/dist/accept are each optional; cross-check needs accept_out.
+bool slm_frame_eligible(slm_ctx *ctx, int64_t nq, int64_t nt, bool cross);
+int slm_frame_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                   int32_t ratio_num, int32_t ratio_den, int32_t cross_check, uint64_t *keys_out, int32_t *idx_out,
+                   int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
 
 // ---- finalize / merge / compaction (finalize.cu) -------------------------------------------------
 // keys uint64[n][2] -> idx/dist/accept.  rev_keys (optional) = reverse search keys uint64[nt][2] used
@@ -145,5 +157,8 @@ int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_fram
 // ---- bag-of-words follow-on (bow.cu) ------------------------------------------------------------------
 int slm_bow_hist_impl(slm_ctx *ctx, const int32_t *idx, int64_t n, int32_t idx_stride, int32_t n_words, int32_t *hist,
                       cudaStream_t stream);
+// binary vocabulary training, update step (vocab.cu)
+int slm_vocab_update_impl(slm_ctx *ctx, const uint32_t *desc, int64_t n, const int32_t *words, int32_t stride,
+                          uint32_t *vocab, int32_t n_words, int32_t *counts_out, int32_t *changed_out, cudaStream_t stream);
 int slm_chi2_scan_impl(slm_ctx *ctx, const int32_t *hq, const int32_t *db, int64_t n_db, int32_t k, double *dist,
                        int32_t *best_idx, double *best_val, cudaStream_t stream);

@@ -18,11 +18,11 @@ VARIANTS = {"auto": 0, "popc": 1, "tensor": 2, "bmma": 3}
 # every symbol include/slammatch.h declares (tests check the library exports all of them)
 SYMBOLS = (
     "slm_last_error", "slm_version", "slm_create", "slm_destroy", "slm_set_variant", "slm_last_variant",
-    "slm_launch_count",
+    "slm_launch_count", "slm_last_kernel",
     "slm_profile_enable", "slm_profile_read",
     "slm_knn2", "slm_knn2_keys", "slm_knn2_filter", "slm_knn2_batched", "slm_merge_top2",
     "slm_exchange_merge", "slm_knn2_exchange",
-    "slm_compact_matches", "slm_gather_rows", "slm_bow_hist", "slm_chi2_scan",
+    "slm_compact_matches", "slm_gather_rows", "slm_bow_hist", "slm_chi2_scan", "slm_vocab_update",
     "slm_knn2_host",
 )
 
@@ -61,6 +61,7 @@ def load():
         lib.slm_set_variant.argtypes = [vp, ctypes.c_int]
         lib.slm_last_variant.argtypes = [vp]
         lib.slm_launch_count.argtypes = [vp]
+        lib.slm_last_kernel.argtypes = [vp]
         lib.slm_launch_count.restype = i64
         lib.slm_profile_enable.argtypes = [vp, ctypes.c_int]
         lib.slm_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
@@ -76,10 +77,12 @@ def load():
         lib.slm_gather_rows.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp, vp]
         lib.slm_bow_hist.argtypes = [vp, vp, i64, i32, i32, vp, vp]
         lib.slm_chi2_scan.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp]
+        lib.slm_vocab_update.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp, vp, vp]
         lib.slm_knn2_host.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]
         for name in SYMBOLS:
-            if name not in ("slm_last_error", "slm_launch_count"):
+            if name not in ("slm_last_error", "slm_launch_count", "slm_last_kernel"):
                 getattr(lib, name).restype = ctypes.c_int
+        lib.slm_last_kernel.restype = ctypes.c_char_p
         _lib = lib
         return lib
 
@@ -106,6 +109,10 @@ class Context:
     def last_variant(self) -> str:
         v = int(self.lib.slm_last_variant(self.handle))
         return {n: k for k, n in VARIANTS.items()}.get(v, "auto")
+
+    def last_kernel(self) -> str:
+        """Name of the distance kernel the last search launched."""
+        return (self.lib.slm_last_kernel(self.handle) or b"").decode()
 
     def launch_count(self) -> int:
         return int(self.lib.slm_launch_count(self.handle))

@@ -17,7 +17,64 @@ from . import _lib
 from .matcher import knn2
 
 
+def vocab_init(descriptors, k: int, seed: int = 0) -> np.ndarray:
+    """Initial vocabulary: k distinct rows of the descriptor pool (seeded numpy Generator, rows kept in pool order)."""
+    d = np.ascontiguousarray(descriptors)
+    if not 1 <= k <= d.shape[0]:
+        raise ValueError("need 1 <= k <= number of descriptors")
+    rows = np.random.default_rng(seed).choice(d.shape[0], size=k, replace=False)
+    return d[np.sort(rows)].copy()
+
+
+def train_vocabulary(descriptors, k: int, iters: int = 10, seed: int = 0, device: int = 0, init=None):
+    """``KMeans(n_clusters=k).fit(dpool)`` of bag_of_words.py:14,20, re-specified for binary descriptors
+    (SURVEY.md D6 / section 8(f) rank 3): Lloyd iterations in Hamming space (k-majority).
+
+    Assignment is the kNN kernel itself (nearest word, lowest index on ties -- for the config-4 shape, 1M
+    descriptors x 64k words, that is the tensor-pipe kernel); the update is ``slm_vocab_update`` (bitwise majority
+    per word, ties keep the old bit, empty words keep their centroid).  Everything stays on the GPU; the only host
+    read per iteration is the 4-byte "centroids changed" count.  Returns ``(vocabulary uint8[k, 32], iterations)``.
+    """
+    import torch
+    dev = torch.device("cuda", device)
+    if hasattr(descriptors, "is_cuda"):
+        d = descriptors.to(dev).contiguous()
+        pool = None
+    else:
+        pool = np.ascontiguousarray(descriptors)
+        if pool.dtype != np.uint8 or pool.ndim != 2 or pool.shape[1] != 32:
+            raise ValueError("descriptors must be uint8[n, 32]")
+        d = torch.from_numpy(pool).to(dev)
+    if init is None:
+        init = vocab_init(pool if pool is not None else d.cpu().numpy(), k, seed)
+    init = np.ascontiguousarray(init)
+    if init.shape != (k, 32) or init.dtype != np.uint8:
+        raise ValueError("init must be uint8[k, 32]")
+    vocab = torch.from_numpy(init).to(dev)
+    ctx = _lib.context(device)
+    changed = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    it = 0
+    for it in range(1, iters + 1):
+        idx, _, _ = knn2(d, vocab, ratio=None)
+        _lib.check(ctx.lib.slm_vocab_update(ctx.handle, d.data_ptr(), d.shape[0], idx.data_ptr(), 2, vocab.data_ptr(),
+                                            k, None, changed.data_ptr(), stream))
+        if int(changed.item()) == 0:
+            break
+    return vocab.cpu().numpy(), it
+
+
 class BoW:
+    @classmethod
+    def fit(cls, descriptor_list, n_clusters: int = 50, iters: int = 10, seed: int = 0, device: int = 0):
+        """The reference's ``BoW(n_clusters).train(imgs)`` (bag_of_words.py:16-21) from per-image descriptors:
+        pool them, train the vocabulary, then store one word histogram per image."""
+        pool = np.concatenate([np.ascontiguousarray(d) for d in descriptor_list])
+        vocab, _ = train_vocabulary(pool, n_clusters, iters=iters, seed=seed, device=device)
+        bow = cls(vocab, device=device, capacity=max(len(descriptor_list), 8))
+        bow.train(descriptor_list)
+        return bow
+
     def __init__(self, vocabulary, device: int = 0, capacity: int = 1024):
         import torch
         vocabulary = np.ascontiguousarray(vocabulary)

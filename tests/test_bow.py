@@ -65,3 +65,61 @@ def test_chi2_scan_first_minimum_wins_and_sum_order_is_numpys():
         torch.cuda.synchronize()
         assert np.array_equal(dist.cpu().numpy(), want), k            # every distance bit-exact
         assert int(bi.item()) == int(np.argmin(want)) == 20 and float(bv.item()) == float(np.min(want))
+
+
+def test_vocab_update_rule_majority_ties_and_empty_words():
+    """The k-majority update rule of the oracle itself on a hand-made case (CPU only)."""
+    desc = np.zeros((5, 32), np.uint8)
+    desc[0, 0] = 0b0000_0111
+    desc[1, 0] = 0b0000_0011
+    desc[2, 0] = 0b0000_0001          # word 0 members: bit0 3/3, bit1 2/3, bit2 1/3
+    desc[3, 1] = 0xFF
+    desc[4, 1] = 0x00                 # word 1 members: every bit of byte 1 tied 1/2
+    vocab = np.zeros((3, 32), np.uint8)
+    vocab[1, 1] = 0b1010_1010         # ties keep these bits
+    vocab[2, 5] = 0x5A                # no members: stays
+    new, counts, changed = orc.np_vocab_update(desc, np.array([0, 0, 0, 1, 1]), vocab)
+    assert counts.tolist() == [3, 2, 0]
+    assert new[0, 0] == 0b0000_0011 and new[1, 1] == 0b1010_1010 and new[2, 5] == 0x5A
+    assert changed == 1
+
+
+@pytest.mark.gpu
+def test_vocab_update_and_training_equal_the_oracle():
+    """slm_vocab_update against np_vocab_update (random assignments incl. empty and tied words), then whole training
+    runs: same initial words, same iterations, bit-identical vocabulary."""
+    import torch
+    import slammatch
+    from slammatch import _lib
+    from slammatch.bow import train_vocabulary, BoW
+    ctx = slammatch.context(0)
+    rng = np.random.default_rng(11)
+    for n, k in ((1, 1), (2, 1), (500, 7), (4000, 50), (3000, 1500), (20000, 300)):
+        desc = synth.uniform(n, 50 + n)
+        vocab = synth.uniform(k, 60 + k)
+        words = rng.integers(-1, k + 1, size=(n, 2)).astype(np.int32)     # -1 and k are out of range: skipped
+        words[: n // 3, 0] = rng.integers(0, max(1, k // 4), size=n // 3)  # some crowded words
+        want, want_counts, want_changed = orc.np_vocab_update(desc, words[:, 0], vocab)
+        dd, wd, vd = torch.from_numpy(desc).cuda(), torch.from_numpy(words).cuda(), torch.from_numpy(vocab).cuda()
+        counts = torch.full((k,), -1, dtype=torch.int32, device="cuda")
+        changed = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+        _lib.check(ctx.lib.slm_vocab_update(ctx.handle, dd.data_ptr(), n, wd.data_ptr(), 2, vd.data_ptr(), k,
+                                            counts.data_ptr(), changed.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(counts.cpu().numpy(), want_counts), (n, k)
+        assert np.array_equal(vd.cpu().numpy(), want), (n, k)
+        assert int(changed.item()) == want_changed, (n, k)
+    # clustered data: 40 prototypes x noisy copies; the trained words must equal the oracle's, bit for bit
+    protos = synth.uniform(40, 5)
+    noise = np.packbits(rng.random((6000, 256)) < 0.08, axis=1, bitorder="little")
+    pool = protos[rng.integers(0, 40, 6000)] ^ noise
+    for k, iters in ((40, 8), (64, 5), (9, 6)):
+        want, want_it = orc.np_train_vocabulary(pool, k, iters=iters, seed=3, knn=orc.c_knn2)
+        got, got_it = train_vocabulary(pool, k, iters=iters, seed=3)
+        assert got_it == want_it and np.array_equal(got, want), (k, iters)
+    # the reference's BoW(n_clusters).train(...) flow from per-image descriptors
+    imgs = [pool[i * 100:(i + 1) * 100] for i in range(20)]
+    bow = BoW.fit(imgs, n_clusters=50, iters=4, seed=1)
+    vocab50, _ = orc.np_train_vocabulary(np.concatenate(imgs), 50, iters=4, seed=1, knn=orc.c_knn2)
+    for i in (0, 7, 19):
+        assert np.array_equal(bow.db[i], orc.np_bow_hist(orc.c_knn2(imgs[i], vocab50)[0][:, 0], 50))
