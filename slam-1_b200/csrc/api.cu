@@ -286,13 +286,34 @@ int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t 
     SLM_TRY(slm_prof_mark(ctx, stream, SLM_TAG_CALL_BEGIN));
     SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys, stream));
     const uint64_t *rev = nullptr;
-    if (cross) {
+    int rev_by_query = 0;
+    if (cross && nq < nt) {
+        // Reverse search, reduced: query i can only be mutual with its own best match, so only the <= nq train rows
+        // best(i) are searched against the queries (nq x nq comparisons instead of nt x nq; lowest query index wins
+        // ties either way).  Frame-sized nq: one launch that also applies the ratio test and writes the outputs.
+        const int fwd_variant = ctx->last_variant;
+        const char *fwd_kernel = ctx->last_kernel;
+        if (ctx->variant == SLM_VARIANT_AUTO && slm_frame_eligible(ctx, nq, nq, false)) {
+            SLM_TRY(slm_frame_revcheck(ctx, q, nq, t, base, ratio_num, ratio_den, keys, idx_out, dist_out, accept_out, stream));
+            ctx->last_variant = fwd_variant;
+            ctx->last_kernel = fwd_kernel;
+            return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
+        }
+        SLM_TRY(slm_buf_reserve(ctx, &ctx->misc, (size_t)nq * 32));
+        SLM_TRY(slm_buf_reserve(ctx, &ctx->rev, (size_t)nq * 16));
+        uint32_t *best_rows = reinterpret_cast<uint32_t *>(ctx->misc.p);
+        SLM_TRY(slm_gather_best_rows(ctx, keys, nq, base, t, best_rows, stream));
+        SLM_TRY(knn2_keys_dispatch(ctx, best_rows, nq, q, nq, 0, reinterpret_cast<uint64_t *>(ctx->rev.p), stream));
+        rev = reinterpret_cast<const uint64_t *>(ctx->rev.p);
+        rev_by_query = 1;
+    } else if (cross) {
         // reverse search: every train row against all queries (lowest query index wins ties)
         SLM_TRY(slm_buf_reserve(ctx, &ctx->rev, (size_t)nt * 16));
         SLM_TRY(knn2_keys_dispatch(ctx, t, nt, q, nq, 0, reinterpret_cast<uint64_t *>(ctx->rev.p), stream));
         rev = reinterpret_cast<const uint64_t *>(ctx->rev.p);
     }
-    SLM_TRY(slm_finalize(ctx, keys, nq, ratio_num, ratio_den, rev, nt, base, idx_out, dist_out, accept_out, stream));
+    SLM_TRY(slm_finalize(ctx, keys, nq, ratio_num, ratio_den, rev, nt, base, idx_out, dist_out, accept_out, stream,
+                         rev_by_query));
     return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
 }
 

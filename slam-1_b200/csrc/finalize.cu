@@ -11,7 +11,7 @@ namespace {
 
 __global__ void finalize_kernel(const unsigned long long *keys, long long n, int ratio_num, int ratio_den,
                                 const unsigned long long *rev_keys, long long nt, long long base,
-                                int *idx_out, int *dist_out, unsigned char *accept_out)
+                                int *idx_out, int *dist_out, unsigned char *accept_out, int rev_by_query)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -24,11 +24,25 @@ __global__ void finalize_kernel(const unsigned long long *keys, long long n, int
     if (accept_out) {
         bool ok = ratio_num > 0 ? (has1 && has2 && (long long)ratio_den * d1 < (long long)ratio_num * d2) : has1;
         if (ok && rev_keys != nullptr) {
-            long long j = (long long)i1 - base;
-            ok = j >= 0 && j < nt && (long long)(rev_keys[2 * j] & 0xFFFFFFFFull) == i;
+            if (rev_by_query) {
+                ok = (long long)(rev_keys[2 * i] & 0xFFFFFFFFull) == i;
+            } else {
+                long long j = (long long)i1 - base;
+                ok = j >= 0 && j < nt && (long long)(rev_keys[2 * j] & 0xFFFFFFFFull) == i;
+            }
         }
         accept_out[i] = ok ? 1 : 0;
     }
+}
+
+// Rows of the train set that are some query's best match, in query order (input of the reduced reverse search).
+__global__ void gather_best_rows_kernel(const unsigned long long *keys, long long n, long long base, const uint4 *t,
+                                        uint4 *out)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 16-byte half row
+    if (g >= 2 * n) return;
+    const unsigned long long k = keys[2 * (g >> 1)];
+    out[g] = k == kKeyNone ? make_uint4(0, 0, 0, 0) : __ldg(t + 2 * ((long long)(k & 0xFFFFFFFFull) - base) + (g & 1));
 }
 
 __global__ void merge_keys_kernel(const unsigned long long *gathered, int n_shards, long long nq,
@@ -223,12 +237,25 @@ int slm_gather(slm_ctx *ctx, const void *src, int32_t row_bytes, const int32_t *
 
 int slm_finalize(slm_ctx *ctx, const uint64_t *keys, int64_t n, int32_t ratio_num, int32_t ratio_den,
                  const uint64_t *rev_keys, int64_t nt, int64_t train_index_base, int32_t *idx_out,
-                 int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream)
+                 int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream, int rev_by_query)
 {
     if (n <= 0) return SLM_OK;
     finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
         reinterpret_cast<const unsigned long long *>(keys), n, ratio_num, ratio_den,
-        reinterpret_cast<const unsigned long long *>(rev_keys), nt, train_index_base, idx_out, dist_out, accept_out);
+        reinterpret_cast<const unsigned long long *>(rev_keys), nt, train_index_base, idx_out, dist_out, accept_out,
+        rev_by_query);
+    SLM_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return SLM_OK;
+}
+
+int slm_gather_best_rows(slm_ctx *ctx, const uint64_t *keys, int64_t n, int64_t train_index_base, const uint32_t *t,
+                         uint32_t *out, cudaStream_t stream)
+{
+    if (n <= 0) return SLM_OK;
+    gather_best_rows_kernel<<<(unsigned)((2 * n + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const unsigned long long *>(keys), n, train_index_base, reinterpret_cast<const uint4 *>(t),
+        reinterpret_cast<uint4 *>(out));
     SLM_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return SLM_OK;

@@ -55,6 +55,10 @@ struct FrameParams {
     int *idx_out, *dist_out;
     unsigned char *accept_out;
     unsigned *done_counter;           // zero between launches (cross only)
+    // reverse-check mode (fwd_keys != nullptr): "query" i of direction 0 is train row best(i) of a finished forward
+    // search, the "train" side is the query set; the result says whether query i is the best match of its own best
+    // match, and the final stage writes idx / dist / accept from the forward keys
+    const unsigned long long *fwd_keys;
 };
 
 __device__ __forceinline__ void top2_insert(unsigned &k1, unsigned &k2, unsigned key)
@@ -105,7 +109,12 @@ __global__ void __launch_bounds__(WARPS * 32) knn2_frame_kernel(const FrameParam
 #pragma unroll
     for (int k = 0; k < KQ; ++k) {
         const int qi = min(group * QC + k * 32 + lane, d.nq - 1);
-        const uint4 *src = reinterpret_cast<const uint4 *>(d.q + (long long)qi * 8);
+        long long qrow = qi;
+        if (p.fwd_keys) {
+            const unsigned long long fk = p.fwd_keys[2 * (long long)qi];
+            qrow = fk == kKeyNone ? 0 : (long long)(fk & 0xFFFFFFFFull) - p.base;
+        }
+        const uint4 *src = reinterpret_cast<const uint4 *>(d.q + qrow * 8);
         const uint4 lo = __ldg(src), hi = __ldg(src + 1);
         qr[k][0] = lo.x; qr[k][1] = lo.y; qr[k][2] = lo.z; qr[k][3] = lo.w;
         qr[k][4] = hi.x; qr[k][5] = hi.y; qr[k][6] = hi.z; qr[k][7] = hi.w;
@@ -176,7 +185,11 @@ __global__ void __launch_bounds__(WARPS * 32) knn2_frame_kernel(const FrameParam
     }
     if (tid < QC) {
         const int qi = group * QC + tid;
-        if (qi < d.nq) {
+        if (qi < d.nq && p.fwd_keys) {
+            const ulonglong2 fk = reinterpret_cast<const ulonglong2 *>(p.fwd_keys)[qi];
+            const bool mutual = fk.x != kKeyNone && k1 != kFrameNone && (int)(k1 & kFrameIdxMask) == qi;
+            write_result(fk.x, fk.y, qi, p.ratio_num, p.ratio_den, mutual, p.idx_out, p.dist_out, p.accept_out);
+        } else if (qi < d.nq) {
             const long long base = dirn == 0 ? p.base : 0;
             const unsigned long long g1 = widen_key(k1, base), g2 = widen_key(k2, base);
             unsigned long long *keys = dirn == 0 ? p.keys_out : p.rev_keys;
@@ -280,11 +293,10 @@ bool slm_frame_eligible(slm_ctx *ctx, int64_t nq, int64_t nt, bool cross)
     return pl.est_clk >= 0 && pl.est_clk <= (cross ? 2 : 1) * ctx->frame_max_clk;
 }
 
-int slm_frame_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
-                   int32_t ratio_num, int32_t ratio_den, int32_t cross_check, uint64_t *keys_out, int32_t *idx_out,
-                   int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream)
+static int frame_run(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                     int32_t ratio_num, int32_t ratio_den, bool cross, const uint64_t *fwd_keys, uint64_t *keys_out,
+                     int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream)
 {
-    const bool cross = cross_check != 0 && accept_out != nullptr;
     const FramePlan pl = cached_plan(ctx, nq, nt, cross);
     if (pl.est_clk < 0) return slm_fail(SLM_ERR_UNSUPPORTED, "shape %lld x %lld is outside the frame kernel's range",
                                         (long long)nq, (long long)nt);
@@ -296,6 +308,7 @@ int slm_frame_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *
     p.ratio_num = ratio_num; p.ratio_den = ratio_den;
     p.keys_out = reinterpret_cast<unsigned long long *>(keys_out);
     p.idx_out = idx_out; p.dist_out = dist_out; p.accept_out = accept_out;
+    p.fwd_keys = reinterpret_cast<const unsigned long long *>(fwd_keys);
     const int qc = 32 * pl.kq;
     const int s0 = pl.splits[0], s1 = pl.splits[1];
     p.dir[0] = FrameDir{q, t, (int)nq, (int)nt, (int)((nq + qc - 1) / qc), s0, (int)((nt + s0 - 1) / s0)};
@@ -327,13 +340,33 @@ int slm_frame_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *
     }
     p.tickets = reinterpret_cast<unsigned *>(ctx->tickets.p);
 
-    SLM_TRY(slm_prof_begin(ctx, stream));
+    // (the reverse check after a tensor-pipe search is not that call's dominant kernel: no profile bracket)
+    if (!fwd_keys) SLM_TRY(slm_prof_begin(ctx, stream));
     cudaError_t e;
     if (ctx->frame_warps == 16) e = launch_frame<16>(pl.kq, (unsigned)items, p, stream);
     else if (ctx->frame_warps == 4) e = launch_frame<4>(pl.kq, (unsigned)items, p, stream);
     else e = launch_frame<8>(pl.kq, (unsigned)items, p, stream);
     if (e != cudaSuccess) return slm_fail(SLM_ERR_CUDA, "frame kernel launch failed: %s", cudaGetErrorString(e));
-    SLM_TRY(slm_prof_end(ctx, stream));
+    if (!fwd_keys) SLM_TRY(slm_prof_end(ctx, stream));
     ctx->launches += 1;
     return SLM_OK;
+}
+
+int slm_frame_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                   int32_t ratio_num, int32_t ratio_den, int32_t cross_check, uint64_t *keys_out, int32_t *idx_out,
+                   int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream)
+{
+    return frame_run(ctx, q, nq, t, nt, base, ratio_num, ratio_den, cross_check != 0 && accept_out != nullptr, nullptr,
+                     keys_out, idx_out, dist_out, accept_out, stream);
+}
+
+// Cross-check after a forward search that ran elsewhere (tensor pipe): only the <= nq train rows that ARE somebody's
+// best match can be mutual, so the reverse search is best(i) x all queries -- nq x nq instead of nt x nq -- and
+// for frame-sized nq it is this kernel, which also applies the ratio test and writes the final outputs.
+int slm_frame_revcheck(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t base, int32_t ratio_num,
+                       int32_t ratio_den, const uint64_t *fwd_keys, int32_t *idx_out, int32_t *dist_out,
+                       uint8_t *accept_out, cudaStream_t stream)
+{
+    return frame_run(ctx, t, nq, q, nq, base, ratio_num, ratio_den, false, fwd_keys, nullptr, idx_out, dist_out,
+                     accept_out, stream);
 }

@@ -99,12 +99,20 @@ int slm_frame_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *
                    int32_t ratio_num, int32_t ratio_den, int32_t cross_check, uint64_t *keys_out, int32_t *idx_out,
                    int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
 
+int slm_frame_revcheck(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t base, int32_t ratio_num,
+                       int32_t ratio_den, const uint64_t *fwd_keys, int32_t *idx_out, int32_t *dist_out,
+                       uint8_t *accept_out, cudaStream_t stream);
+
 // ---- finalize / merge / compaction (finalize.cu) -------------------------------------------------
 // keys uint64[n][2] -> idx/dist/accept.  rev_keys (optional) = reverse search keys uint64[nt][2] used
 // for the cross-check; train_index_base is subtracted from the forward index to address it.
+// rev_by_query != 0: rev_keys is uint64[n][2], entry i = reverse search of query i's best train row over all queries.
 int slm_finalize(slm_ctx *ctx, const uint64_t *keys, int64_t n, int32_t ratio_num, int32_t ratio_den,
                  const uint64_t *rev_keys, int64_t nt, int64_t train_index_base, int32_t *idx_out,
-                 int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
+                 int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream, int rev_by_query = 0);
+// out[i] = train row best(i) of the forward keys (zeros when query i has no neighbour): uint32[n][8]
+int slm_gather_best_rows(slm_ctx *ctx, const uint64_t *keys, int64_t n, int64_t train_index_base, const uint32_t *t,
+                         uint32_t *out, cudaStream_t stream);
 int slm_merge_keys(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int64_t nq,
                    uint64_t *keys_out, cudaStream_t stream);
 int slm_merge_finalize(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int64_t nq, int32_t ratio_num,

@@ -101,3 +101,29 @@ def test_auto_policy_uses_frame_kernel_for_the_reference_shape_only():
     q, t = synth.planted(2000, 200000, 2)
     slammatch.knn2(q, t)
     assert ctx.last_kernel() == "knn2_tc2_kernel"
+
+
+@pytest.mark.parametrize("variant", ["auto", "tensor", "popc"])
+@pytest.mark.parametrize("nq,nt", [(2000, 20000), (300, 301), (1000, 40000), (5000, 9000), (64, 3000)])
+def test_reduced_reverse_search_cross_check(variant, nq, nt):
+    """Cross-check with nq < nt searches only the train rows that are some query's best match (nq x nq) -- through
+    the frame kernel for frame-sized nq under AUTO, through gather + search + finalize otherwise; duplicated train
+    rows and heavy ties make the lowest-index rules on both sides matter."""
+    import torch
+    ctx = slammatch.context(0)
+    if nq % 2:
+        q, t = synth.heavy_ties(nq, nq + 5), synth.heavy_ties(nt, nt + 6)
+    else:
+        q, t = synth.planted(nq, nt, nq + nt)
+        t = synth.with_duplicates(t, 3, 0.3)
+        q[1::7] = q[0]                      # duplicated queries: only the lowest query index can be mutual
+    oi, od = orc.c_knn2(q, t)
+    for ratio in ((7, 10), None):
+        want = (orc.c_ratio(od, *ratio) if ratio else np.ones(nq, np.uint8)) & orc.c_cross_check(q, t, oi)
+        try:
+            i, d, a = slammatch.knn2(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), ratio=ratio,
+                                     cross_check=True, variant=variant, train_index_base=1000)
+        finally:
+            ctx.set_variant("auto")
+        assert np.array_equal(i.cpu().numpy(), oi + 1000) and np.array_equal(d.cpu().numpy(), od)
+        assert np.array_equal(a.cpu().numpy(), want), (variant, nq, nt, ratio)
