@@ -6,7 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <numeric>
+#include <vector>
 
 #include "slm_internal.cuh"
 
@@ -161,6 +164,9 @@ int slm_create(int device, slm_ctx **ctx_out)
         int v = atoi(e);
         if (v >= 1) ctx->max_cpg = v;
     }
+    ctx->no_frame_refine = getenv("SLM_TC_NO_FRAME_REFINE") != nullptr;
+    if (const char *e = getenv("SLM_TC_CHAIN")) ctx->tc_chain_max = atoi(e);
+    if (const char *e = getenv("SLM_TC_CHAIN_MIN")) ctx->tc_chain_min = atoi(e);
     if (const char *e = getenv("SLM_FRAME_MAX_CLK")) ctx->frame_max_clk = atoll(e);
     if (const char *e = getenv("SLM_FRAME_WARPS")) {
         int v = atoi(e);
@@ -341,16 +347,55 @@ int slm_knn2_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_frames, int64
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t rows = n_pairs * n_per_frame;
     SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)rows * 16));
-    SLM_TRY(slm_buf_reserve(ctx, &ctx->misc, (size_t)n_pairs * 8));
-    SLM_TRY(pin_reserve(ctx, (size_t)n_pairs * 8));
+    // Chain plan (tensor variant): pairs sorted by query frame, cut into units of <= L pairs that share it, longest
+    // units first.  L keeps ~8 waves of clusters for balance while the cluster start-up is paid once per unit.
+    std::vector<int32_t> sorted, prob, units;
+    if (ctx->tc_chain_max > 1 && n_pairs >= 2 && n_pairs <= 32768) {
+        const int64_t m_tiles = (n_per_frame + 127) / 128, n_gpairs = (m_tiles + 7) / 8;
+        int64_t L = n_pairs * n_gpairs / ((int64_t)(ctx->sm_count / 2) * 8);
+        L = std::max<int64_t>(std::max(1, ctx->tc_chain_min), std::min<int64_t>(L, ctx->tc_chain_max));
+        if (L > 1) {
+            std::vector<int32_t> order((size_t)n_pairs);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(),
+                             [&](int32_t a, int32_t b) { return pairs_host[2 * a] < pairs_host[2 * b]; });
+            sorted.resize((size_t)n_pairs * 2);
+            prob.resize((size_t)n_pairs);
+            for (int64_t k = 0; k < n_pairs; ++k) {
+                sorted[2 * k] = pairs_host[2 * order[k]];
+                sorted[2 * k + 1] = pairs_host[2 * order[k] + 1];
+                prob[k] = order[k];
+            }
+            std::vector<std::pair<int32_t, int32_t>> u;
+            for (int64_t k = 0; k < n_pairs;) {
+                int64_t e = k;
+                while (e < n_pairs && sorted[2 * e] == sorted[2 * k] && e - k < L) ++e;
+                u.emplace_back((int32_t)k, (int32_t)(e - k));
+                k = e;
+            }
+            std::stable_sort(u.begin(), u.end(), [](const auto &a, const auto &b) { return a.second > b.second; });
+            for (const auto &x : u) { units.push_back(x.first); units.push_back(x.second); }
+        }
+    }
+    // one upload: [pairs | sorted pairs | units | prob]  (the int2-read arrays first: 8-byte aligned for any n_pairs)
+    const size_t n_ints = (size_t)n_pairs * 2 + sorted.size() + prob.size() + units.size();
+    SLM_TRY(slm_buf_reserve(ctx, &ctx->misc, n_ints * 4));
+    SLM_TRY(pin_reserve(ctx, n_ints * 4));
     // the pinned copy must not be overwritten while a previous call's H2D is in flight
     SLM_CUDA(cudaEventSynchronize(ctx->ev[0]));
-    memcpy(ctx->pin, pairs_host, (size_t)n_pairs * 8);
-    SLM_CUDA(cudaMemcpyAsync(ctx->misc.p, ctx->pin, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, stream));
+    int32_t *pin = reinterpret_cast<int32_t *>(ctx->pin);
+    memcpy(pin, pairs_host, (size_t)n_pairs * 8);
+    if (!units.empty()) {
+        memcpy(pin + 2 * n_pairs, sorted.data(), sorted.size() * 4);
+        memcpy(pin + 4 * n_pairs, units.data(), units.size() * 4);
+        memcpy(pin + 4 * n_pairs + units.size(), prob.data(), prob.size() * 4);
+    }
+    SLM_CUDA(cudaMemcpyAsync(ctx->misc.p, ctx->pin, n_ints * 4, cudaMemcpyHostToDevice, stream));
     SLM_CUDA(cudaEventRecord(ctx->ev[0], stream));
+    const int32_t *dev = reinterpret_cast<const int32_t *>(ctx->misc.p);
+    slm_chain chain{dev + 2 * n_pairs, dev + 4 * n_pairs + units.size(), dev + 4 * n_pairs, (int)(units.size() / 2)};
     uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
-    SLM_TRY(slm_batched_knn2_keys(ctx, desc, n_per_frame, reinterpret_cast<const int32_t *>(ctx->misc.p), n_pairs,
-                                  keys, stream));
+    SLM_TRY(slm_batched_knn2_keys(ctx, desc, n_per_frame, dev, n_pairs, keys, stream, units.empty() ? nullptr : &chain));
     return slm_finalize(ctx, keys, rows, ratio_num, ratio_den, nullptr, 0, 0, idx_out, dist_out, accept_out, stream);
 }
 

@@ -18,16 +18,17 @@ int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
 }
 
 int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
-                          int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream)
+                          int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain)
 {
     // grid.y / grid.z carry the pair index: chunk long pair lists
     const int64_t kMaxPairs = 32768;
+    if (n_pairs > kMaxPairs) chain = nullptr;     // chain units index the whole (sorted) pair list
     for (int64_t p0 = 0; p0 < n_pairs; p0 += kMaxPairs) {
         int64_t n = n_pairs - p0 < kMaxPairs ? n_pairs - p0 : kMaxPairs;
         if (ctx->variant == SLM_VARIANT_TENSOR ||
             (ctx->variant == SLM_VARIANT_AUTO && n_per_frame * n_per_frame >= kAutoTensorMinCmp))
             SLM_TRY(slm_tc_knn2_keys_batched(ctx, desc, n_per_frame, pairs_dev + 2 * p0, n,
-                                             keys_out + 2 * p0 * n_per_frame, stream));
+                                             keys_out + 2 * p0 * n_per_frame, stream, chain));
         else
             SLM_TRY(slm_popc_knn2_keys_batched(ctx, desc, n_per_frame, pairs_dev + 2 * p0, n,
                                                keys_out + 2 * p0 * n_per_frame, stream));

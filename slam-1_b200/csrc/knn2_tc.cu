@@ -64,6 +64,12 @@ struct TcParams {
                                   // unit c walks ranges c, c + cpg, c + 2 cpg, ... of its group
     int rpe, n_epochs;            // ranges per candidate epoch (rpe * range_tiles <= 4096 tiles), epochs per unit
     float2 *cand;                 // [n_prob][nq][cpg * n_epochs][2 sets]: best two chunk keys per epilogue set
+    // Chained batches (2-CTA kernel, config 3): grid.y indexes UNITS = runs of pairs that share the query frame.  The
+    // cluster expands that frame's query tiles once and walks the train frames of the run back to back (one
+    // candidate flush per pair), instead of paying the cluster start-up once per pair.
+    const int32_t *chain_pairs;   // device int32[n_prob][2], pairs sorted by query frame (nullptr = not chained)
+    const int32_t *chain_prob;    // device int32[n_prob]: caller's pair index of every sorted pair (output slot)
+    const int32_t *chain_units;   // device int32[n_units][2] = (first sorted pair, number of pairs)
 };
 
 struct TcBarriers {
@@ -288,7 +294,7 @@ struct TcBarriers2 {
     uint32_t tmem_base;
 };
 
-template <int MT>
+template <int MT, bool CHAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_tc2_kernel(TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -305,11 +311,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
 
     const uint32_t *q = p.q;
     const uint32_t *t = p.t;
-    if (p.desc != nullptr) {
+    int link_first = 0, n_links = 1;              // chained batch: sorted pairs [link_first, link_first + n_links)
+    if constexpr (CHAIN) {
+        const int2 cu = reinterpret_cast<const int2 *>(p.chain_units)[blockIdx.y];
+        link_first = cu.x;
+        n_links = cu.y;
+        q = p.desc + (long long)p.chain_pairs[2 * link_first] * p.frame_words;
+    } else if (p.desc != nullptr) {
         int2 pr = reinterpret_cast<const int2 *>(p.pairs)[blockIdx.y];
         q = p.desc + (long long)pr.x * p.frame_words;
         t = p.desc + (long long)pr.y * p.frame_words;
     }
+    // train rows / output slot of link l (identity when not chained)
+    auto link_train = [&](int l) -> const uint32_t * {
+        if constexpr (CHAIN) return p.desc + (long long)p.chain_pairs[2 * (link_first + l) + 1] * p.frame_words;
+        else return t;
+    };
+    auto link_prob = [&](int l) -> int {
+        if constexpr (CHAIN) return p.chain_prob[link_first + l];
+        else return (int)blockIdx.y;
+    };
+    if constexpr (!CHAIN) n_links = 1;
 
     const int q_first = group * (MT * kTileM);
     // query tiles this CTA really owns (0 for the idle half) and the number of MMA chains per train tile,
@@ -368,7 +390,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
         const int set = warp >> 2, quad = warp & 3;
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         const int n_slots = p.cpg * p.n_epochs;
-        float2 *cand = p.cand + ((long long)blockIdx.y * p.nq) * n_slots * 2 + (long long)(unit * p.n_epochs) * 2 + set;
+        float2 *cand = nullptr;
         float b1[MT], b2[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) { b1[m] = -FLT_MAX; b2[m] = -FLT_MAX; }
@@ -381,7 +403,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
                 b2[m] = -FLT_MAX;
             }
         };
-        int job = 0, epoch = 0, lt = 0, j = 0;     // lt = tiles seen in this epoch, j = ranges walked
+        int job = 0;
+        for (int link = 0; link < n_links; ++link) {
+        cand = p.cand + ((long long)link_prob(link) * p.nq) * n_slots * 2 + (long long)(unit * p.n_epochs) * 2 + set;
+        int epoch = 0, lt = 0, j = 0;     // lt = tiles seen in this epoch, j = ranges walked
         for (int r = unit; r < p.n_ranges; r += p.cpg, ++j) {
             if (j > 0 && j % p.rpe == 0) { flush(epoch); ++epoch; lt = 0; }
             const int col_first = r * p.range_tiles * kTileN;
@@ -450,34 +475,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
             }
         }
         for (; epoch < p.n_epochs; ++epoch) flush(epoch);     // remaining epochs are written as "none"
+        }
     } else if (warp < mma_warp) {
         // ===================== expanders: this CTA's query tiles + its half of every train tile =====================
         const int et = tid - kEpiThreads;   // 0..95
         const uint32_t sB_addr = tc::smem_u32(sB);
         // 128 rows per half tile over 96 threads: thread et expands row et, threads 0..31 also row 96 + et
         const bool two_rows = et < 128 - kExp2Threads;
-        auto load_row = [&](int r, int bt, int row_in_half, uint4 &d0, uint4 &d1) {
+        auto load_row = [&](const uint32_t *tl, int r, int bt, int row_in_half, uint4 &d0, uint4 &d1) {
             const int row = min((r * p.range_tiles + bt) * kTileN + (int)rank * 128 + row_in_half, p.nt - 1);
-            const uint4 *src = reinterpret_cast<const uint4 *>(t + (long long)row * 8);
+            const uint4 *src = reinterpret_cast<const uint4 *>(tl + (long long)row * 8);
             d0 = __ldg(src);
             d1 = __ldg(src + 1);
         };
         uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, m0 = n0, m1 = n0;
+        const uint32_t *t_link = link_train(0);
         if (unit < p.n_ranges) {
-            load_row(unit, 0, et, n0, n1);
-            if (two_rows) load_row(unit, 0, et + kExp2Threads, m0, m1);
+            load_row(t_link, unit, 0, et, n0, n1);
+            if (two_rows) load_row(t_link, unit, 0, et + kExp2Threads, m0, m1);
         }
         int s = 0, ph = 0;
+        for (int link = 0; link < n_links; ++link) {
+        const uint32_t *t_next = link + 1 < n_links ? link_train(link + 1) : nullptr;
         for (int r = unit; r < p.n_ranges; r += p.cpg) {
             const int n_tiles = tiles_in_range(r);
             for (int bt = 0; bt < n_tiles; ++bt) {
                 const uint4 c0 = n0, c1 = n1, e0 = m0, e1 = m1;
-                // prefetch the rows of the next tile this cluster will see (possibly in its next range)
+                // prefetch the rows of the next tile this cluster will see (possibly in its next range, or in the
+                // next train frame of a chained batch)
                 int r2 = r, bt2 = bt + 1;
+                const uint32_t *t2 = t_link;
                 if (bt2 == n_tiles) { r2 = r + p.cpg; bt2 = 0; }
+                if (r2 >= p.n_ranges && t_next != nullptr) { t2 = t_next; r2 = unit; }
                 if (r2 < p.n_ranges) {
-                    load_row(r2, bt2, et, n0, n1);
-                    if (two_rows) load_row(r2, bt2, et + kExp2Threads, m0, m1);
+                    load_row(t2, r2, bt2, et, n0, n1);
+                    if (two_rows) load_row(t2, r2, bt2, et + kExp2Threads, m0, m1);
                 }
                 tc::mbar_wait_backoff(&bars->b_empty[s], ph ^ 1, 20 + s, 200);
                 tc::expand_row_to_smem(sB_addr + (uint32_t)s * kBHalfBytes, et, c0, c1);
@@ -487,6 +519,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
                 if (++s == kBStages2) { s = 0; ph ^= 1; }
             }
         }
+        t_link = t_next;
+        }
     } else {
         // ===================== MMA issuer: leader CTA; the warp stays converged, one elected lane issues ==========
         if (rank == 0) {
@@ -495,6 +529,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
             tc::mbar_wait_cluster(&bars->a_full, 0, 30);
             tc::tc_fence_after();
             int job = 0, s = 0, ph = 0;
+            for (int link = 0; link < n_links; ++link)
             for (int r = unit; r < p.n_ranges; r += p.cpg) {
                 const int n_tiles = tiles_in_range(r);
                 for (int bt = 0; bt < n_tiles; ++bt) {
@@ -694,6 +729,87 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
     }
 }
 
+// Refine for batches of frame-sized problems (config 3).  tc_refine_kernel reads every query's 64 candidate rows
+// straight from L2: 2 KB per query, 8 GB for 2016 pairs x 2000 queries -- L2-bandwidth bound (0.9 ms, as long as the
+// tensor kernel itself).  Here one CTA owns one pair, stages the pair's whole train frame in shared memory once
+// (64 KB for 2000 rows) and re-scores all of the pair's queries from there; what is left is the POPC pipe.
+// Requires one candidate slot per query (cpg * n_epochs == 1) and nt * 32 bytes of shared memory.
+constexpr int kRefineFrameThreads = 512;
+__global__ void __launch_bounds__(kRefineFrameThreads) tc_refine_frame_kernel(TcParams p, unsigned long long *keys_out)
+{
+    extern __shared__ __align__(16) uint4 s_rows[];      // nt rows x 2
+    constexpr int G = 8;
+    const int prob = blockIdx.x;
+    const int2 pr = reinterpret_cast<const int2 *>(p.pairs)[prob];
+    const uint32_t *q = p.desc + (long long)pr.x * p.frame_words;
+    const uint4 *t4 = reinterpret_cast<const uint4 *>(p.desc + (long long)pr.y * p.frame_words);
+    // low halves of all rows first, then the high halves: the 8 lanes of a group read 8 consecutive rows, i.e.
+    // 128 contiguous bytes per LDS.128 quarter-warp -- conflict-free (32-byte row stride would be 2-way)
+    for (int i = threadIdx.x; i < 2 * p.nt; i += kRefineFrameThreads) s_rows[(i & 1) * p.nt + (i >> 1)] = __ldg(t4 + i);
+    __syncthreads();
+    const int sub = threadIdx.x % G, grp = threadIdx.x / G;
+    const float4 *cand4 = reinterpret_cast<const float4 *>(p.cand) + (long long)prob * p.nq;
+    for (int q0 = 0; q0 < p.nq; q0 += kRefineFrameThreads / G) {
+        const int qi = q0 + grp;
+        const bool live = qi < p.nq;
+        const int qc = live ? qi : 0;
+        // ---- phase 1: the best two chunks out of the four candidates (two epilogue sets x best / second) ----
+        const float4 c4 = __ldg(cand4 + qc);
+        const float cf[4] = {c4.x, c4.y, c4.z, c4.w};
+        unsigned long long c1 = 0, c2 = 0;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+            if (cf[ci] > -1.0e30f) {
+                const int ki = (int)cf[ci] + kKeyBias;
+                const unsigned gchunk = (unsigned)(kChunkMask - (ki & kChunkMask));   // one unit, one epoch: chunk counter = global chunk
+                top2_insert_max(c1, c2, ((unsigned long long)((ki >> kChunkBits) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk));
+            }
+        }
+        const unsigned ga = c1 ? 0xFFFFFFFFu - (unsigned)(c1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+        const unsigned gb = c2 ? 0xFFFFFFFFu - (unsigned)(c2 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+        const unsigned glo = min(ga, gb), ghi = max(ga, gb);
+        // ---- phase 2: exact re-scoring of those 64 rows from shared memory ----
+        const uint4 *qs = reinterpret_cast<const uint4 *>(q + (long long)qc * 8);
+        const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
+        unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const unsigned g = s == 0 ? glo : ghi;
+            if (g == 0xFFFFFFFFu) continue;
+#pragma unroll
+            for (int j = 0; j < 32 / G; ++j) {
+                const int pos = j * G + sub;
+                const int row = (int)g * kChunk + pos;
+                if (row < p.nt) {
+                    const uint4 ta = s_rows[row], tb = s_rows[p.nt + row];
+                    const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                                       __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+                    const unsigned key = (d << 6) | (unsigned)(s * 32 + pos);
+                    const unsigned m = max(k1, key);
+                    k1 = min(k1, key);
+                    k2 = min(k2, m);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const unsigned o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
+            const unsigned m = max(k1, o1);
+            k1 = min(k1, o1);
+            k2 = min(min(k2, o2), m);
+        }
+        if (live && sub == 0) {
+            auto widen = [&](unsigned k) -> unsigned long long {
+                if (k == 0xFFFFFFFFu) return kKeyNone;
+                const unsigned pos = k & 63u;
+                const long long row = (long long)(pos < 32 ? glo : ghi) * kChunk + (pos & 31u);
+                return ((unsigned long long)(k >> 6) << 32) | (unsigned long long)row;
+            };
+            reinterpret_cast<ulonglong2 *>(keys_out)[(long long)prob * p.nq + qi] = make_ulonglong2(widen(k1), widen(k2));
+        }
+    }
+}
+
 template <int MT>
 int launch_tc(const TcParams &p, int n_prob, cudaStream_t stream)
 {
@@ -711,26 +827,32 @@ int launch_tc(const TcParams &p, int n_prob, cudaStream_t stream)
     return SLM_OK;
 }
 
-template <int MT>
-int launch_tc2(const TcParams &p, int n_prob, cudaStream_t stream)
+template <int MT, bool CHAIN>
+int launch_tc2_impl(const TcParams &p, int n_prob, cudaStream_t stream)
 {
     const size_t smem = (size_t)MT * kATileBytes + kBStages2 * kBHalfBytes + sizeof(TcBarriers2) + 64;
     static bool configured[64] = {};
     int dev = 0;
     SLM_CUDA(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
-        SLM_CUDA(cudaFuncSetAttribute(knn2_tc2_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SLM_CUDA(cudaFuncSetAttribute(knn2_tc2_kernel<MT, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev & 63] = true;
     }
     const int n_gpairs = (p.n_groups + 1) / 2;
     dim3 grid((unsigned)(2 * n_gpairs * p.cpg), (unsigned)n_prob);
-    knn2_tc2_kernel<MT><<<grid, kThreads2, smem, stream>>>(p);
+    knn2_tc2_kernel<MT, CHAIN><<<grid, kThreads2, smem, stream>>>(p);
     SLM_CUDA(cudaGetLastError());
     return SLM_OK;
 }
 
+template <int MT>
+int launch_tc2(const TcParams &p, int n_prob, cudaStream_t stream)
+{
+    return p.chain_pairs ? launch_tc2_impl<MT, true>(p, n_prob, stream) : launch_tc2_impl<MT, false>(p, n_prob, stream);
+}
+
 int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_out, cudaStream_t stream,
-           const slm_exchange *exchange = nullptr)
+           const slm_exchange *exchange = nullptr, const slm_chain *chain = nullptr)
 {
     ctx->last_variant = SLM_VARIANT_TENSOR;
     p.n_prob = n_prob;
@@ -801,6 +923,15 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     }
     if (n_prob > 65535) return slm_fail(SLM_ERR_UNSUPPORTED, "at most 65535 problems per launch");
 
+    // Chained batch: short train frames (one cluster per query-group pair walks a whole frame in one epoch) whose
+    // pairs share query frames -- grid.y runs over the units instead of the pairs.
+    int grid_y = n_prob;
+    if (chain && two_cta && p.cpg == 1 && p.n_epochs == 1 && chain->n_units > 0 && chain->n_units < n_prob) {
+        p.chain_pairs = chain->pairs_sorted;
+        p.chain_prob = chain->prob;
+        p.chain_units = chain->units;
+        grid_y = chain->n_units;
+    }
     const size_t cand_bytes = (size_t)n_prob * (size_t)p.cpg * p.n_epochs * 2 * (size_t)p.nq * sizeof(float2);
     SLM_TRY(slm_buf_reserve(ctx, &ctx->scratch, cand_bytes));
     p.cand = reinterpret_cast<float2 *>(ctx->scratch.p);
@@ -809,10 +940,10 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     SLM_TRY(slm_prof_begin(ctx, stream));
     if (two_cta) {
         switch (p.mt) {
-        case 1: SLM_TRY(launch_tc2<1>(p, n_prob, stream)); break;
-        case 2: SLM_TRY(launch_tc2<2>(p, n_prob, stream)); break;
-        case 3: SLM_TRY(launch_tc2<3>(p, n_prob, stream)); break;
-        default: SLM_TRY(launch_tc2<4>(p, n_prob, stream)); break;
+        case 1: SLM_TRY(launch_tc2<1>(p, grid_y, stream)); break;
+        case 2: SLM_TRY(launch_tc2<2>(p, grid_y, stream)); break;
+        case 3: SLM_TRY(launch_tc2<3>(p, grid_y, stream)); break;
+        default: SLM_TRY(launch_tc2<4>(p, grid_y, stream)); break;
         }
     } else {
         switch (p.mt) {
@@ -825,7 +956,20 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     const long long n_q = (long long)n_prob * p.nq;
     slm_exchange ex{};
     if (exchange) ex = *exchange;
-    if (p.cpg * p.n_epochs * 4 <= 32) {   // few candidates per query (many queries, short train sets): 8 lanes each
+    const size_t frame_smem = (size_t)p.nt * 32;
+    if (p.desc != nullptr && !exchange && p.cpg * p.n_epochs == 1 && n_prob >= ctx->sm_count && frame_smem <= 200 * 1024 &&
+        !ctx->no_frame_refine) {
+        // batch of frame-sized problems: one CTA per pair, train frame staged in shared memory
+        static bool configured[64] = {};
+        int dev = 0;
+        SLM_CUDA(cudaGetDevice(&dev));
+        if (!configured[dev & 63]) {
+            SLM_CUDA(cudaFuncSetAttribute(tc_refine_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured[dev & 63] = true;
+        }
+        tc_refine_frame_kernel<<<(unsigned)n_prob, kRefineFrameThreads, frame_smem, stream>>>(
+            p, reinterpret_cast<unsigned long long *>(keys_out));
+    } else if (p.cpg * p.n_epochs * 4 <= 32) {   // few candidates per query (many queries, short train sets): 8 lanes each
         tc_refine_kernel<8><<<(unsigned)((n_q + 31) / 32), 256, 0, stream>>>(
             p, base, reinterpret_cast<unsigned long long *>(keys_out), ex);
     } else {                          // many ranges (long train sets): a full warp per query
@@ -858,11 +1002,11 @@ int slm_tc_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint
 }
 
 int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
-                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream)
+                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain)
 {
     TcParams p{};
     p.q = nullptr; p.t = nullptr; p.desc = desc; p.pairs = pairs_dev;
     p.frame_words = n_per_frame * 8;
     p.nq = (int)n_per_frame; p.nt = (int)n_per_frame;
-    return tc_run(ctx, p, (int)n_pairs, 0, keys_out, stream);
+    return tc_run(ctx, p, (int)n_pairs, 0, keys_out, stream, nullptr, chain);
 }

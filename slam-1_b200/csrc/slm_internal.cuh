@@ -25,6 +25,9 @@ struct slm_ctx {
     int epoch_tiles = 4096;   // tiles per candidate epoch (SLM_TC_EPOCH_TILES shrinks it so tests reach the epoch logic)
     int max_cpg = 1 << 30;    // cap on clusters per query-group pair (SLM_TC_MAX_CPG, tests only)
     int force_1cta = 0;   // debugging / A-B: run the single-CTA tcgen05 kernel even when CTA pairs apply
+    int tc_chain_max = 8;  // batched calls: at most this many pairs of one query frame per cluster (SLM_TC_CHAIN; <= 1 = off)
+    int no_frame_refine = 0;   // SLM_TC_NO_FRAME_REFINE: batched calls keep the L2-fed refine kernel (A/B)
+    int tc_chain_min = 1;  // ... and at least this many when the run is long enough (SLM_TC_CHAIN_MIN; tests)
     int frame_warps = 8;               // warps per CTA of the frame kernel: 4, 8 or 16 (SLM_FRAME_WARPS)
     long long frame_max_clk = 26000;   // AUTO prefers the single-launch frame kernel up to this estimated cost, twice that with
                                        // cross-check (SLM_FRAME_MAX_CLK; 0 = never; calibration in profiles/r1_calib_frame.txt)
@@ -149,8 +152,16 @@ int slm_tc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t
 // peer's buffer; its last block publishes the flags, waits for the peers and merges (no separate kernel).
 int slm_tc_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
                          const slm_exchange &ex, cudaStream_t stream);
+// Chained batch (config 3): the caller's pairs sorted by query frame and cut into units of pairs that share it
+// (all device arrays; see TcParams in knn2_tc.cu).  Optional: nullptr = every pair is its own launch item.
+struct slm_chain {
+    const int32_t *pairs_sorted;   // int32[n_pairs][2]
+    const int32_t *prob;           // int32[n_pairs]: caller's pair index of every sorted pair
+    const int32_t *units;          // int32[n_units][2] = (first sorted pair, number of pairs)
+    int n_units;
+};
 int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
-                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream);
+                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain = nullptr);
 
 // ---- variant B: b1 AND.POPC mma.sync tiles (knn2_bmma.cu; emulated by ptxas on sm_100a) -----------
 int slm_bmma_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
@@ -160,7 +171,7 @@ int slm_bmma_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
 int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
                        int64_t base, uint64_t *keys_out, cudaStream_t stream);
 int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
-                          int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream);
+                          int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain = nullptr);
 
 // ---- bag-of-words follow-on (bow.cu) ------------------------------------------------------------------
 int slm_bow_hist_impl(slm_ctx *ctx, const int32_t *idx, int64_t n, int32_t idx_stride, int32_t n_words, int32_t *hist,

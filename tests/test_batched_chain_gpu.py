@@ -1,0 +1,107 @@
+"""Chained batches (config 3): pairs that share a query frame are walked by one resident cluster (query tiles
+expanded once, one candidate flush per pair).  Forced on for small batches through SLM_TC_CHAIN_MIN and checked
+pair by pair against the oracle -- shuffled pair order, repeated pairs, both orientations, ragged frame sizes."""
+import os
+
+import numpy as np
+import pytest
+
+from slammatch import _lib, synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(**env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return _lib.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+def _batched(ctx, desc, pairs, ratio=(7, 10)):
+    import torch
+    frames, n = desc.shape[0], desc.shape[1]
+    dd = torch.from_numpy(desc).cuda()
+    P = pairs.shape[0]
+    idx = torch.full((P, n, 2), -9, dtype=torch.int32, device="cuda")
+    dist = torch.full((P, n, 2), -9, dtype=torch.int32, device="cuda")
+    acc = torch.full((P, n), 9, dtype=torch.uint8, device="cuda")
+    _lib.check(ctx.lib.slm_knn2_batched(ctx.handle, dd.data_ptr(), frames, n, pairs.ctypes.data, P, ratio[0], ratio[1],
+                                        idx.data_ptr(), dist.data_ptr(), acc.data_ptr(), None))
+    torch.cuda.synchronize()
+    return idx.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy()
+
+
+@pytest.mark.parametrize("n", [129, 300, 777, 1100])
+@pytest.mark.parametrize("chain_min", [2, 3, 8])
+def test_chained_batches_equal_oracle_pair_by_pair(n, chain_min):
+    ctx = _ctx(SLM_TC_CHAIN_MIN=chain_min)
+    ctx.set_variant("tensor")
+    frames = 7
+    rng = np.random.default_rng(n + chain_min)
+    base = synth.heavy_ties(n, 60 + n) if n == 129 else synth.uniform(n, 50 + n)
+    desc = np.stack([base ^ np.packbits(rng.random((n, 256)) < 0.04 * (f + 1), axis=1, bitorder="little")
+                     for f in range(frames)])
+    pairs = [(i, j) for i in range(frames) for j in range(i + 1, frames)]
+    pairs += [(5, 1), (5, 0), (3, 3), (0, 6), (0, 6)]            # reversed, self, repeated
+    pairs = np.array(pairs, dtype=np.int32)[rng.permutation(len(pairs))]
+    idx, dist, acc = _batched(ctx, desc, pairs)
+    for p, (a, b) in enumerate(pairs):
+        oi, od = orc.c_knn2(desc[a], desc[b])
+        assert np.array_equal(idx[p], oi) and np.array_equal(dist[p], od), (n, chain_min, p, a, b)
+        assert np.array_equal(acc[p], orc.c_ratio(od, 7, 10)), (n, chain_min, p)
+    ctx.close()
+
+
+def test_chain_plan_is_invisible_in_the_results():
+    """Same batch with chaining off and on: byte-identical outputs."""
+    frames, n = 9, 520
+    rng = np.random.default_rng(3)
+    desc = np.stack([synth.uniform(n, 900 + f) for f in range(frames)])
+    desc[4, :200] = desc[2, 100:300]                      # shared rows between frames: exact duplicates
+    pairs = np.array([(i, j) for i in range(frames) for j in range(frames) if i != j], dtype=np.int32)
+    off, on = _ctx(SLM_TC_CHAIN=0), _ctx(SLM_TC_CHAIN_MIN=5)
+    for c in (off, on):
+        c.set_variant("tensor")
+    a, b = _batched(off, desc, pairs), _batched(on, desc, pairs)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert a[2].sum() > 0
+    off.close()
+    on.close()
+
+
+@pytest.mark.parametrize("n", [260, 1000])
+def test_frame_refine_kernel_many_pairs(n):
+    """>= 148 pairs switch the refine step to one CTA per pair with the train frame in shared memory; with and
+    without chaining, against the oracle and against the L2-fed refine kernel."""
+    frames = 18
+    rng = np.random.default_rng(n)
+    base = synth.uniform(n, 70 + n)
+    desc = np.stack([base ^ np.packbits(rng.random((n, 256)) < 0.03 * (1 + f % 4), axis=1, bitorder="little")
+                     for f in range(frames)])
+    desc[7, : n // 2] = desc[3, n // 4: n // 4 + n // 2]          # exact duplicates across frames
+    pairs = np.array([(i, j) for i in range(frames) for j in range(i + 1, frames)], dtype=np.int32)   # 153 pairs
+    ref = None
+    for env in (dict(SLM_TC_CHAIN_MIN=4), dict(SLM_TC_CHAIN=0), dict(SLM_TC_NO_FRAME_REFINE=1, SLM_TC_CHAIN=0)):
+        ctx = _ctx(**env)
+        ctx.set_variant("tensor")
+        out = _batched(ctx, desc, pairs)
+        ctx.close()
+        if ref is None:
+            ref = out
+            for p in range(0, pairs.shape[0], 7):
+                a, b = pairs[p]
+                oi, od = orc.c_knn2(desc[a], desc[b])
+                assert np.array_equal(out[0][p], oi) and np.array_equal(out[1][p], od), (n, p)
+                assert np.array_equal(out[2][p], orc.c_ratio(od, 7, 10)), (n, p)
+        else:
+            for x, y in zip(ref, out):
+                assert np.array_equal(x, y), env
