@@ -62,6 +62,7 @@ struct TcParams {
     int range_tiles, n_ranges;    // the train set is cut into n_ranges ranges of range_tiles 256-row tiles
     int cpg;                      // CTAs (1-CTA kernel) / clusters (2-CTA kernel) per query group (pair):
                                   // unit c walks ranges c, c + cpg, c + 2 cpg, ... of its group
+    int chunk;                    // candidate chunk width in train rows: 32, or 16 in chained batches (refine kernels)
     int rpe, n_epochs;            // ranges per candidate epoch (rpe * range_tiles <= 4096 tiles), epochs per unit
     float2 *cand;                 // [n_prob][nq][cpg * n_epochs][2 sets]: best two chunk keys per epilogue set
     // Chained batches (2-CTA kernel, config 3): grid.y indexes UNITS = runs of pairs that share the query frame.  The
@@ -91,6 +92,19 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32])
     }
     m0 = fmaxf(fmaxf(m0, __uint_as_float(v[28])), __uint_as_float(v[29]));
     m1 = fmaxf(fmaxf(m1, __uint_as_float(v[30])), __uint_as_float(v[31]));
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// maximum of 16 of the 32 loaded columns (half-width candidate chunks of chained batches): 8 FMNMX3
+template <int O>
+__device__ __forceinline__ float max16(const uint32_t (&v)[32])
+{
+    float m0 = fmaxf(fmaxf(__uint_as_float(v[O + 0]), __uint_as_float(v[O + 1])), __uint_as_float(v[O + 2]));
+    float m1 = fmaxf(fmaxf(__uint_as_float(v[O + 3]), __uint_as_float(v[O + 4])), __uint_as_float(v[O + 5]));
+    float m2 = fmaxf(fmaxf(__uint_as_float(v[O + 6]), __uint_as_float(v[O + 7])), __uint_as_float(v[O + 8]));
+    float m3 = fmaxf(fmaxf(__uint_as_float(v[O + 9]), __uint_as_float(v[O + 10])), __uint_as_float(v[O + 11]));
+    m0 = fmaxf(fmaxf(m0, __uint_as_float(v[O + 12])), __uint_as_float(v[O + 13]));
+    m1 = fmaxf(fmaxf(m1, __uint_as_float(v[O + 14])), __uint_as_float(v[O + 15]));
     return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
@@ -414,8 +428,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
             const int n_tiles = (col_end - col_first + kTileN - 1) / kTileN;
             for (int bt = 0; bt < n_tiles; ++bt, ++lt) {
                 const int valid_cols = min(kTileN, col_end - (col_first + bt * kTileN));
-                const int n_chunks = (valid_cols + kChunk - 1) / kChunk;
-                const float chunk_bias = (float)(kChunkMask - lt * kChunksPerTile);
+                // Chained batches track 16-column candidate chunks (CH = 16): the refine pass re-scores two chunks per
+                // query and is the second-largest cost of a batch of frame-sized problems, so halving the chunk
+                // halves it for ~20 % more FMNMX here; long single problems keep 32 (their refine is negligible).
+                constexpr int CH = CHAIN ? 16 : kChunk;
+                constexpr int kCPT = kTileN / CH;
+                const int n_chunks = (valid_cols + CH - 1) / CH;
+                const float chunk_bias = (float)(kChunkMask - lt * kCPT);
+                auto track = [&](float &t1, float &t2, float key) {
+                    t2 = fmaxf(t2, fminf(t1, key));
+                    t1 = fmaxf(t1, key);
+                };
 #pragma unroll
                 for (int m = 0; m < MT; ++m) {
                     if (m < mt_pair) {
@@ -423,7 +446,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
                         tc::mbar_wait(&bars->acc_full[ab], (job >> 1) & 1, 10 + ab);
                         tc::tc_fence_after();
                         const uint32_t acc_addr = lane_addr + ab * kTileN + set * kChunk;
-                        if (m < mt_mine && n_chunks == kChunksPerTile) {
+                        if (m < mt_mine && n_chunks == kCPT) {
                             // full tile: all four TMEM loads of this warp in flight at once; the accumulator is
                             // handed back as soon as they have landed, BEFORE the reduction -- with two accumulators
                             // the MMA may only run ahead by one job, so the hand-back latency is on the critical path
@@ -438,31 +461,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) knn2_t
                             tc::pin_regs(v3);
                             tc::tc_fence_before();
                             tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
-                            const float base_bias = chunk_bias - (float)set;
-                            float key = fmaf(max32(v0), kKeyScale, base_bias);
-                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
-                            b1[m] = fmaxf(b1[m], key);
-                            key = fmaf(max32(v1), kKeyScale, base_bias - 2.0f);
-                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
-                            b1[m] = fmaxf(b1[m], key);
-                            key = fmaf(max32(v2), kKeyScale, base_bias - 4.0f);
-                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
-                            b1[m] = fmaxf(b1[m], key);
-                            key = fmaf(max32(v3), kKeyScale, base_bias - 6.0f);
-                            b2[m] = fmaxf(b2[m], fminf(b1[m], key));
-                            b1[m] = fmaxf(b1[m], key);
+                            if constexpr (CH == kChunk) {
+                                const float base_bias = chunk_bias - (float)set;
+                                track(b1[m], b2[m], fmaf(max32(v0), kKeyScale, base_bias));
+                                track(b1[m], b2[m], fmaf(max32(v1), kKeyScale, base_bias - 2.0f));
+                                track(b1[m], b2[m], fmaf(max32(v2), kKeyScale, base_bias - 4.0f));
+                                track(b1[m], b2[m], fmaf(max32(v3), kKeyScale, base_bias - 6.0f));
+                            } else {
+                                // 32-column block b = set + 2 cc holds the 16-column chunks 2 b and 2 b + 1
+                                const float base_bias = chunk_bias - (float)(2 * set);
+                                track(b1[m], b2[m], fmaf(max16<0>(v0), kKeyScale, base_bias));
+                                track(b1[m], b2[m], fmaf(max16<16>(v0), kKeyScale, base_bias - 1.0f));
+                                track(b1[m], b2[m], fmaf(max16<0>(v1), kKeyScale, base_bias - 4.0f));
+                                track(b1[m], b2[m], fmaf(max16<16>(v1), kKeyScale, base_bias - 5.0f));
+                                track(b1[m], b2[m], fmaf(max16<0>(v2), kKeyScale, base_bias - 8.0f));
+                                track(b1[m], b2[m], fmaf(max16<16>(v2), kKeyScale, base_bias - 9.0f));
+                                track(b1[m], b2[m], fmaf(max16<0>(v3), kKeyScale, base_bias - 12.0f));
+                                track(b1[m], b2[m], fmaf(max16<16>(v3), kKeyScale, base_bias - 13.0f));
+                            }
                         } else {
                             if (m < mt_mine) {
                                 // last, partial tile of the train set: only chunks that contain valid columns count
 #pragma unroll
                                 for (int cc = 0; cc < kChunksPerTile / 2; ++cc) {
-                                    const int c = 2 * cc + set;
-                                    if (c < n_chunks) {
+                                    const int blk = 2 * cc + set;          // 32-column block of the accumulator
+                                    if (blk * kChunk < valid_cols) {
                                         uint32_t v[32];
                                         tc::tmem_ld32(acc_addr + cc * 2 * kChunk, v);
-                                        const float key = fmaf(max32(v), kKeyScale, chunk_bias - (float)c);
-                                        b2[m] = fmaxf(b2[m], fminf(b1[m], key));
-                                        b1[m] = fmaxf(b1[m], key);
+                                        if constexpr (CH == kChunk) {
+                                            track(b1[m], b2[m], fmaf(max32(v), kKeyScale, chunk_bias - (float)blk));
+                                        } else {
+                                            track(b1[m], b2[m], fmaf(max16<0>(v), kKeyScale, chunk_bias - (float)(2 * blk)));
+                                            if (2 * blk + 1 < n_chunks)
+                                                track(b1[m], b2[m], fmaf(max16<16>(v), kKeyScale, chunk_bias - (float)(2 * blk + 1)));
+                                        }
                                     }
                                 }
                             }
@@ -613,9 +645,10 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
             const int ki = (int)key + kKeyBias;
             const int lc = kChunkMask - (ki & kChunkMask);
             const int slot = ci >> 2, unit = slot / p.n_epochs, epoch = slot % p.n_epochs;
-            const int lt = lc >> 3;                                   // tile counter inside the epoch
+            const int cpt = kTileN / p.chunk;                         // chunks per tile: 8 (or 16 in chained batches)
+            const int lt = lc / cpt;                                  // tile counter inside the epoch
             const int range = unit + (epoch * p.rpe + lt / p.range_tiles) * p.cpg;
-            const unsigned gchunk = (unsigned)((range * p.range_tiles + lt % p.range_tiles) * kChunksPerTile + (lc & 7));
+            const unsigned gchunk = (unsigned)((range * p.range_tiles + lt % p.range_tiles) * cpt + (lc & (cpt - 1)));
             top2_insert_max(c1, c2, ((unsigned long long)((ki >> kChunkBits) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk));
         }
     };
@@ -645,8 +678,8 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
 #pragma unroll
         for (int j = 0; j < 32 / G; ++j) {
             const int pos = j * G + sub;
-            const long long row = (long long)g * kChunk + pos;
-            if (row < p.nt) {
+            const long long row = (long long)g * p.chunk + pos;
+            if (pos < p.chunk && row < p.nt) {
                 const uint4 *ts = reinterpret_cast<const uint4 *>(t + row * 8);
                 const uint4 ta = __ldg(ts), tb = __ldg(ts + 1);
                 const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
@@ -670,7 +703,7 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
         auto widen = [&](unsigned k) -> unsigned long long {
             if (k == 0xFFFFFFFFu) return kKeyNone;
             const unsigned pos = k & 63u;
-            const long long row = (long long)(pos < 32 ? glo : ghi) * kChunk + (pos & 31u);
+            const long long row = (long long)(pos < 32 ? glo : ghi) * p.chunk + (pos & 31u);
             return ((unsigned long long)(k >> 6) << 32) | (unsigned long long)(base + row);
         };
         const ulonglong2 kk = make_ulonglong2(widen(k1), widen(k2));
@@ -779,8 +812,8 @@ __global__ void __launch_bounds__(kRefineFrameThreads) tc_refine_frame_kernel(Tc
 #pragma unroll
             for (int j = 0; j < 32 / G; ++j) {
                 const int pos = j * G + sub;
-                const int row = (int)g * kChunk + pos;
-                if (row < p.nt) {
+                const int row = (int)g * p.chunk + pos;
+                if (pos < p.chunk && row < p.nt) {
                     const uint4 ta = s_rows[row], tb = s_rows[p.nt + row];
                     const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
                                        __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
@@ -802,7 +835,7 @@ __global__ void __launch_bounds__(kRefineFrameThreads) tc_refine_frame_kernel(Tc
             auto widen = [&](unsigned k) -> unsigned long long {
                 if (k == 0xFFFFFFFFu) return kKeyNone;
                 const unsigned pos = k & 63u;
-                const long long row = (long long)(pos < 32 ? glo : ghi) * kChunk + (pos & 31u);
+                const long long row = (long long)(pos < 32 ? glo : ghi) * p.chunk + (pos & 31u);
                 return ((unsigned long long)(k >> 6) << 32) | (unsigned long long)row;
             };
             reinterpret_cast<ulonglong2 *>(keys_out)[(long long)prob * p.nq + qi] = make_ulonglong2(widen(k1), widen(k2));
@@ -926,7 +959,10 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     // Chained batch: short train frames (one cluster per query-group pair walks a whole frame in one epoch) whose
     // pairs share query frames -- grid.y runs over the units instead of the pairs.
     int grid_y = n_prob;
-    if (chain && two_cta && p.cpg == 1 && p.n_epochs == 1 && chain->n_units > 0 && chain->n_units < n_prob) {
+    p.chunk = kChunk;
+    if (chain && two_cta && p.cpg == 1 && p.n_epochs == 1 && chain->n_units > 0 && chain->n_units < n_prob &&
+        n_tiles <= kMaxEpochTiles / 2) {
+        p.chunk = 16;      // the chained instantiation tracks 16-column candidate chunks
         p.chain_pairs = chain->pairs_sorted;
         p.chain_prob = chain->prob;
         p.chain_units = chain->units;
