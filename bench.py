@@ -367,6 +367,21 @@ def ours(args, w, cfg_id):
     e2e_val = cmp_per_step * jobs * e2e_steps / float(t_e.item()) / 1e9
     out_bytes = (P * nq if args.workload == "c3" else nq) * 17
 
+    # The object-level drop-in call the unmodified reference makes (tracking.py:22): matcher.knnMatch(des1, des2, k=2)
+    # returning tuples of cv2.DMatch -- same copies as e2e plus the construction of 2 * nq result objects.
+    matcher_line = None
+    if world == 1 and args.workload in ("c1", "c2"):
+        m = slammatch.Matcher(crossCheck=False, device=local)
+        qn, tn = q_pin.numpy(), t_pin.numpy()
+        for _ in range(2):
+            m.knnMatch(qn, tn, k=2)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rows = m.knnMatch(qn, tn, k=2)
+        dt = (time.perf_counter() - t0) / e2e_steps
+        matcher_line = {"value": cmp_per_step / dt / 1e9, "unit": UNIT, "us_per_call": dt * 1e6, "rows": len(rows),
+                        "api": "slammatch.Matcher().knnMatch(des1, des2, k=2) -> tuple[nq] of tuple[2] of cv2.DMatch"}
+
     # Same call with the train set held in a persistent device-resident collection (OpenCV's matcher.add([...]) +
     # knnMatch(q, k) form; slammatch.KeyframeDB): the DB is uploaded once, outside the timed region, and every step
     # moves only the query descriptors in and the results out.  Reported NEXT TO e2e, never instead of it.
@@ -490,7 +505,7 @@ def ours(args, w, cfg_id):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
                     "steps": e2e_steps, "api": "slammatch.knn2(host arrays) -> slm_knn2_host" if not (sharded or args.workload == "c3")
                     else "pinned host -> device copy + device entry points + result read-back",
-                    "resident_db": resident},
+                    "resident_db": resident, "matcher_knnMatch": matcher_line},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -545,6 +545,30 @@ int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t
     int32_t *idx_dev = reinterpret_cast<int32_t *>(base + q_b + t_b);
     int32_t *dist_dev = reinterpret_cast<int32_t *>(base + q_b + t_b + i_b);
     uint8_t *acc_dev = base + q_b + t_b + 2 * i_b;
+    // Frame-to-frame shapes (the reference's own call: ~1000 x 1000) are all latency.  Inputs are packed into
+    // one pinned block and travel in a single H2D copy; the one-launch frame kernel writes idx / dist / accept
+    // straight into pinned host memory (mapped into the device address space under UVA), so there is no D2H
+    // copy at all: memcpy in, 1 copy, 1 kernel, 1 synchronize, memcpy out.
+    const bool cross = cross_check != 0 && accept_out != nullptr && nt > 0;
+    if (ctx->variant == SLM_VARIANT_AUTO && nt > 0 && (size_t)(nq + nt) * 32 <= (512u << 10) &&
+        slm_frame_eligible(ctx, nq, nt, cross)) {
+        SLM_TRY(pin_reserve(ctx, q_b + t_b + 2 * i_b + a_b));
+        uint8_t *pin = reinterpret_cast<uint8_t *>(ctx->pin);
+        SLM_CUDA(cudaEventSynchronize(ctx->ev[0]));
+        memcpy(pin, q_host, (size_t)nq * 32);
+        memcpy(pin + q_b, t_host, (size_t)nt * 32);
+        SLM_CUDA(cudaMemcpyAsync(q_dev, pin, q_b + (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+        int32_t *idx_pin = reinterpret_cast<int32_t *>(pin + q_b + t_b);
+        int32_t *dist_pin = reinterpret_cast<int32_t *>(pin + q_b + t_b + i_b);
+        uint8_t *acc_pin = pin + q_b + t_b + 2 * i_b;
+        SLM_TRY(slm_knn2_filter(ctx, q_dev, nq, t_dev, nt, 0, ratio_num, ratio_den, cross_check, idx_pin, dist_pin,
+                                accept_out ? acc_pin : nullptr, s));
+        SLM_CUDA(cudaStreamSynchronize(s));
+        if (idx_out) memcpy(idx_out, idx_pin, (size_t)nq * 8);
+        if (dist_out) memcpy(dist_out, dist_pin, (size_t)nq * 8);
+        if (accept_out) memcpy(accept_out, acc_pin, (size_t)nq);
+        return SLM_OK;
+    }
     // results come back through pinned staging so the D2H copies are truly asynchronous
     SLM_TRY(pin_reserve(ctx, 2 * i_b + a_b));
     uint8_t *pin = reinterpret_cast<uint8_t *>(ctx->pin);

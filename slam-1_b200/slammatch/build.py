@@ -60,7 +60,25 @@ def _compile(src: str, obj: str, verbose: bool) -> str:
     return r.stderr
 
 
+def build_rows(force: bool = False) -> str:
+    """gcc build of slammatch/_rows.c (CPython extension that creates the DMatch result rows in C)."""
+    import sysconfig
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "_rows.c")
+    out = os.path.join(here, "_rows" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        cc = shutil.which("gcc") or shutil.which("cc")
+        if cc is None:
+            raise RuntimeError("gcc not found")
+        cmd = [cc, "-O2", "-shared", "-fPIC", "-Wall", "-I", sysconfig.get_paths()["include"], src, "-o", out]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"gcc failed on _rows.c:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_rows(force)
     os.makedirs(BUILD, exist_ok=True)
     tag = _headers_digest()
     stamp = os.path.join(BUILD, "flags.stamp")

@@ -36,6 +36,40 @@ except Exception:  # pragma: no cover - cv2 is present in the supported images
             self.queryIdx, self.trainIdx, self.imgIdx, self.distance = queryIdx, trainIdx, imgIdx, float(distance)
 
 DMatch = _DMatch
+_fast_rows = None        # (module, payload offset) once verified; False = unavailable
+
+
+def _init_fast_rows():
+    """slammatch._rows builds the DMatch rows in C (what OpenCV's own binding does in C++; ~1 us per object from
+    Python otherwise).  It writes the cv::DMatch payload of freshly allocated objects in place, so the layout is
+    verified here against a normally constructed object and a small end-to-end sample before first use."""
+    global _fast_rows
+    _fast_rows = False
+    if _cv2 is None:
+        return
+    try:
+        try:
+            from . import _rows
+        except ImportError:
+            from . import build as _build
+            _build.build_rows()
+            from . import _rows
+        import struct
+        off = DMatch.__basicsize__ - 16
+        probe = DMatch(7, 8, 9, 2.5)
+        raw = bytes((ctypes.c_ubyte * 16).from_address(id(probe) + off))
+        if struct.unpack("<iiif", raw) != (7, 8, 9, 2.5):
+            return
+        idx = np.array([[3, -1], [5, 6]], dtype=np.int32)
+        dist = np.array([[10, -1], [0, 256]], dtype=np.int32)
+        rows = _rows.make_rows(DMatch, off, idx.ctypes.data, dist.ctypes.data, 0, 2, 2, 0, 0)
+        got = [[(type(m) is DMatch, m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in r] for r in rows]
+        if got == [[(True, 0, 3, 0, 10.0)], [(True, 1, 5, 0, 0.0), (True, 1, 6, 0, 256.0)]]:
+            _fast_rows = (_rows, off)
+    except Exception:
+        _fast_rows = False
+
+
 REFERENCE_RATIO = (7, 10)   # the literal 0.7 at tracking.py:27, keypoint.py:48, Point3D.py:44
 
 
@@ -206,6 +240,21 @@ class Matcher:
 
     @staticmethod
     def _rows(idx, dist, keep, k, offsets):
+        if _fast_rows is None:
+            _init_fast_rows()
+        if _fast_rows:
+            mod, off = _fast_rows
+            idx = np.ascontiguousarray(idx, dtype=np.int32)
+            dist = np.ascontiguousarray(dist, dtype=np.int32)
+            keep_a = np.ascontiguousarray(keep, dtype=np.uint8) if keep is not None else None
+            img = loc = None
+            if offsets is not None:
+                offsets = np.asarray(offsets)
+                img = (np.searchsorted(offsets, np.maximum(idx, 0), side="right") - 1).astype(np.int32)
+                loc = np.ascontiguousarray(idx - offsets[img], dtype=np.int32)
+            return mod.make_rows(DMatch, off, idx.ctypes.data, dist.ctypes.data,
+                                 keep_a.ctypes.data if keep_a is not None else 0, idx.shape[0], int(k),
+                                 img.ctypes.data if img is not None else 0, loc.ctypes.data if loc is not None else 0)
         out = []
         idx_l, dist_l = idx.tolist(), dist.tolist()
         keep_l = keep.tolist() if keep is not None else None
