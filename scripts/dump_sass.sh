@@ -7,10 +7,14 @@ dump() {  # $1 = substring of the mangled name, $2 = output file
     | grep -E "Function :|^\s+/\*[0-9a-f]{4}\*/" | sed -E 's#/\* 0x[0-9a-f]+ \*/##; s/[ \t]+$//' > profiles/sass/$2
   echo "$2: $(wc -l < profiles/sass/$2) lines"
 }
-dump "knn2_tc2_kernelILi4" r1_knn2_tc2_kernel_mt4.sass
+dump "knn2_tc2_kernelILi4ELb0" r1_knn2_tc2_kernel_mt4.sass
 dump "knn2_tc_kernelILi1" r1_knn2_tc_kernel_mt1.sass
 dump "knn2_popc_kernel" r1_knn2_popc_kernel.sass
 dump "knn2_bmma_kernel" r1_knn2_bmma_kernel.sass
 dump "knn2_stream_kernelILi1" r1_knn2_stream_kernel_nq1.sass
 dump "tc_refine_kernelILi32" r1_tc_refine_kernel_g32.sass
+dump "knn2_tc2_kernelILi4ELb1" r1_knn2_tc2_kernel_mt4_chain.sass
+dump "tc_refine_frame_kernel" r1_tc_refine_frame_kernel.sass
+dump "knn2_frame_kernelILi2ELi8" r1_knn2_frame_kernel_kq2_w8.sass
+dump "vocab_majority_kernel" r1_vocab_majority_kernel.sass
 grep -c "UTCQMMA" profiles/sass/r1_knn2_tc2_kernel_mt4.sass
