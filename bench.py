@@ -229,6 +229,11 @@ def ours(args, w, cfg_id):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout, and honours NCCL_DEBUG_FILE only above the VERSION level: raise the
+        # level to WARN and send the log to stderr so that the JSON line is the only thing on stdout
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     sharded = w["sharded"] and world > 1
     if world > 1 and not w["sharded"]:
@@ -526,7 +531,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="auto", choices=["auto", "popc", "tensor", "bmma"])
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvlink"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvlink", "a2a"],
                     help="sharded path: how per-rank keys are exchanged (auto = NVLink peer stores when available)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

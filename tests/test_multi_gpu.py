@@ -52,7 +52,7 @@ def test_nccl_sharded_query_equals_oracle(tmp_path):
     t = synth.with_duplicates(t, 18, 0.2)
     oi, od = orc.c_knn2(q, t)
     for world in sorted({2, n}):
-        for exchange in ("nccl", "auto"):
+        for exchange in ("nccl", "auto", "a2a"):
             mp.spawn(_worker, args=(world, _free_port(), q, t, str(tmp_path), exchange), nprocs=world, join=True)
             print("world", world, "exchange requested", exchange, "used", open(tmp_path / "exchange.txt").read())
             for r in range(world):

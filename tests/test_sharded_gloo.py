@@ -56,6 +56,14 @@ def _worker(rank, world, port, q, t, out_dir):
         bi, bd, ba = sm.knn2(torch.from_numpy(q), query_batch=50)
         assert np.array_equal(np.asarray(bi), np.asarray(idx)) and np.array_equal(np.asarray(bd), np.asarray(dd))
         assert np.array_equal(np.asarray(ba), np.asarray(acc))
+        # all-to-all of query slices + all-gather of merged results (large-query exchange), nq not divisible by world
+        sa = ShardedMatcher(torch.from_numpy(shard), a, local_keys=local_keys, merge=merge, exchange="a2a")
+        ai, ad, aa = sa.knn2(torch.from_numpy(q))
+        assert "all-to-all" in sa.last_exchange
+        assert np.array_equal(np.asarray(ai), np.asarray(idx)) and np.array_equal(np.asarray(ad), np.asarray(dd))
+        assert np.array_equal(np.asarray(aa), np.asarray(acc))
+        ai, ad, aa = sa.knn2(torch.from_numpy(q[:1]))          # fewer queries than ranks
+        assert np.array_equal(np.asarray(ai), np.asarray(idx)[:1]) and np.array_equal(np.asarray(aa), np.asarray(acc)[:1])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx, dist=dd, acc=acc)
     finally:
         dist.destroy_process_group()
