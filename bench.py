@@ -202,12 +202,30 @@ def reference_arm(args, w, cfg_id):
     cmp_per_step = q.shape[0] * t.shape[0]
     val = cmp_per_step * args.steps / dt / 1e9
     sample = f"{q.shape[0]} queries x first {t.shape[0]} train rows of the workload per step"
+    # the same matcher on ONE host thread, on a slice sized for about two seconds
+    single = None
+    try:
+        import cv2
+        n_thr = cv2.getNumThreads()
+        cv2.setNumThreads(1)
+        try:
+            rows_1 = int(max(1, min(t.shape[0], val * 1e9 / max(cores, 1) * 2.0 / q.shape[0])))
+            t1 = time.perf_counter()
+            run(q, t[:rows_1])
+            d1 = max(time.perf_counter() - t1, 1e-6)
+            single = {"value": q.shape[0] * rows_1 / d1 / 1e9, "unit": UNIT, "cores": 1,
+                      "sample": f"{q.shape[0]} queries x first {rows_1} train rows, one pass"}
+        finally:
+            cv2.setNumThreads(n_thr)
+    except Exception:
+        pass
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong" if w["sharded"] else "replicas", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "config": {"workload": w["name"], "sample": sample, "matcher": desc},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "single_thread": single},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
