@@ -165,6 +165,7 @@ int slm_create(int device, slm_ctx **ctx_out)
         if (v >= 1) ctx->max_cpg = v;
     }
     ctx->no_frame_refine = getenv("SLM_TC_NO_FRAME_REFINE") != nullptr;
+    ctx->tc_plan_mt = getenv("SLM_TC_PLAN_MT") != nullptr;
     if (const char *e = getenv("SLM_TC_CHAIN")) ctx->tc_chain_max = atoi(e);
     if (const char *e = getenv("SLM_TC_CHAIN_MIN")) ctx->tc_chain_min = atoi(e);
     if (const char *e = getenv("SLM_FRAME_MAX_CLK")) ctx->frame_max_clk = atoll(e);

@@ -898,6 +898,26 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         // split the query tiles evenly over an even number of groups of at most kMaxMT2 tiles
         int n_groups = 2 * ((m_tiles + 2 * kMaxMT2 - 1) / (2 * kMaxMT2));
         p.mt = (m_tiles + n_groups - 1) / n_groups;
+        if (ctx->tc_plan_mt && n_prob == 1) {
+            // EXPERIMENTAL (SLM_TC_PLAN_MT=1, off by default): also choose the query tiles per CTA.
+            // Fewer tiles per CTA = more, shorter-lived clusters with less to expand at start-up -- better for
+            // mid-size problems (c2: 2000 x 20000) where the start-up dominates.  Start-up model: 6000 + 2000 per
+            // query tile (14000 at 4 tiles, the measured figure); to be calibrated before it becomes the default.
+            const long long slots = ctx->sm_count / 2;
+            double best = 1e300;
+            int best_mt = p.mt;
+            for (int mt = 1; mt <= kMaxMT2; ++mt) {
+                const long long units = ((m_tiles + mt - 1) / mt + 1) / 2;
+                long long cmax = n_tiles < 4 * slots ? n_tiles : 4 * slots;
+                if (cmax > ctx->max_cpg) cmax = ctx->max_cpg;
+                for (long long c = 1; c <= cmax; ++c) {
+                    const long long waves = (units * c + slots - 1) / slots;
+                    const double cost = (double)waves * (6000.0 + 2000.0 * mt + (double)((n_tiles + c - 1) / c) * 1024.0 * mt);
+                    if (cost < best * 0.999) { best = cost; best_mt = mt; }
+                }
+            }
+            p.mt = best_mt;
+        }
         p.n_groups = (m_tiles + p.mt - 1) / p.mt;
         work_units = (p.n_groups + 1) / 2;
     } else {
@@ -914,7 +934,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         // Clusters per unit: minimise  waves x (start-up + tiles per cluster x cycles per tile)  with
         // waves = ceil(units * cpg / cluster slots).  Few units (long train sets) end up as one resident wave,
         // many units as several waves of longer-lived clusters.
-        const double kStartupClk = 14000.0, kTileClk = 1024.0 * p.mt;
+        const double kStartupClk = ctx->tc_plan_mt ? 6000.0 + 2000.0 * p.mt : 14000.0, kTileClk = 1024.0 * p.mt;
         long long cpg = 1;
         double best = 1e300;
         long long cpg_max = n_tiles < 4 * slots ? n_tiles : 4 * slots;

@@ -27,6 +27,7 @@ struct slm_ctx {
     int force_1cta = 0;   // debugging / A-B: run the single-CTA tcgen05 kernel even when CTA pairs apply
     int tc_chain_max = 8;  // batched calls: at most this many pairs of one query frame per cluster (SLM_TC_CHAIN; <= 1 = off)
     int no_frame_refine = 0;   // SLM_TC_NO_FRAME_REFINE: batched calls keep the L2-fed refine kernel (A/B)
+    int tc_plan_mt = 0;    // SLM_TC_PLAN_MT: experimental planner that also picks the query tiles per CTA (off by default)
     int tc_chain_min = 1;  // ... and at least this many when the run is long enough (SLM_TC_CHAIN_MIN; tests)
     int frame_warps = 8;               // warps per CTA of the frame kernel: 4, 8 or 16 (SLM_FRAME_WARPS)
     long long frame_max_clk = 26000;   // AUTO prefers the single-launch frame kernel up to this estimated cost, twice that with

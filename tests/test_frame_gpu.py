@@ -127,3 +127,23 @@ def test_reduced_reverse_search_cross_check(variant, nq, nt):
             ctx.set_variant("auto")
         assert np.array_equal(i.cpu().numpy(), oi + 1000) and np.array_equal(d.cpu().numpy(), od)
         assert np.array_equal(a.cpu().numpy(), want), (variant, nq, nt, ratio)
+
+
+@pytest.mark.skipif(not os.environ.get("SLM_RUN_EXPERIMENTAL"), reason="experimental planner: opt-in (SLM_RUN_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("nq,nt", [(2000, 20000), (300, 5000), (1000, 100000), (4000, 3000), (520, 70001)])
+def test_experimental_mt_planner_parity(nq, nt):
+    """SLM_TC_PLAN_MT=1 lets the tensor kernel's planner also choose the query tiles per CTA (DESIGN.md section 7);
+    off by default until calibrated, so this test only runs on request."""
+    import torch
+    os.environ["SLM_TC_PLAN_MT"] = "1"
+    try:
+        ctx = _lib.Context(0)
+    finally:
+        del os.environ["SLM_TC_PLAN_MT"]
+    ctx.set_variant("tensor")
+    q, t = synth.planted(nq, nt, nq + nt)
+    t = synth.with_duplicates(t, 5, 0.3)
+    i, d, a = _run(ctx, q, t, (7, 10), False)
+    oi, od = orc.c_knn2(q, t)
+    assert np.array_equal(i, oi) and np.array_equal(d, od) and np.array_equal(a, orc.c_ratio(od, 7, 10))
+    ctx.close()
