@@ -38,7 +38,9 @@
  *   thread-local message for the last failure.  `stream` is a cudaStream_t passed as void*
  *   (NULL = legacy default stream).  Device entry points are asynchronous and stream-ordered;
  *   *_host entry points synchronise before returning.  A ctx is not re-entrant: one ctx per
- *   (host thread, device).  The library owns only its workspace (grown on demand); callers own all
+ *   (host thread, device).  The calls of one ctx share its workspace; a call on a different stream
+ *   than the previous one is ordered (on the device) behind everything queued on that stream, so
+ *   results stay correct when the caller switches streams -- calls of one ctx never overlap.  The library owns only its workspace (grown on demand); callers own all
  *   input and output buffers; inputs are never written.  There is NO CPU fallback: without a
  *   CUDA device every compute entry point fails with SLM_ERR_CUDA.
  */
@@ -51,7 +53,7 @@
 extern "C" {
 #endif
 
-#define SLM_VERSION 100           /* major*10000 + minor*100 + patch */
+#define SLM_VERSION 200           /* major*10000 + minor*100 + patch */
 #define SLM_DESC_WORDS 8          /* uint32 words per descriptor */
 #define SLM_DESC_BYTES 32
 #define SLM_KEY_NONE 0xFFFFFFFFFFFFFFFFull
@@ -63,7 +65,8 @@ typedef enum slm_status {
     SLM_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, ratio_den <= 0, ...) */
     SLM_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...) */
     SLM_ERR_NOMEM = -3,       /* workspace allocation failed */
-    SLM_ERR_UNSUPPORTED = -4  /* size beyond the supported range (global index must fit int32) */
+    SLM_ERR_UNSUPPORTED = -4, /* size beyond the supported range (global index must fit int32) */
+    SLM_ERR_TIMEOUT = -5      /* sharded exchange: a peer rank never delivered its keys (reported, never a hang or a trap) */
 } slm_status;
 
 /* Distance-kernel variants (BASELINE.json north_star part (2)). */
@@ -71,7 +74,8 @@ typedef enum slm_variant {
     SLM_VARIANT_AUTO = 0,    /* pick per shape */
     SLM_VARIANT_POPC = 1,    /* LOP3(XOR)+POPC on the integer pipe */
     SLM_VARIANT_TENSOR = 2,  /* +-1 fp8 expansion + tcgen05.mma (TMEM accumulators) */
-    SLM_VARIANT_BMMA = 3     /* b1 AND.POPC mma.sync tiles (emulated by ptxas on sm_100a; kept for the A/B) */
+    SLM_VARIANT_BMMA = 3,    /* b1 AND.POPC mma.sync tiles (emulated by ptxas on sm_100a; kept for the A/B) */
+    SLM_VARIANT_TENSOR4 = 4  /* +-1 e2m1 expansion + tcgen05.mma kind::mxf4 (block scales = 1.0): twice the fp8 rate */
 } slm_variant;
 
 /* Thread-local text of the last error returned on this thread ("" if none). */
@@ -139,32 +143,60 @@ int slm_merge_top2(slm_ctx *ctx, const uint64_t *gathered_keys_dev, int32_t n_sh
                    uint8_t *accept_out_dev, void *stream);
 
 /*
- * NVLink exchange + merge in ONE kernel (the sharded path's replacement for all-gather + slm_merge_top2 when the
- * gather buffers are peer-mapped, e.g. torch symmetric memory over NVLink / NVSwitch).
- *   peer_keys_host[r]  : device address, valid on THIS GPU, of rank r's buffer uint64[2][world][nq_capacity][2]
+ * NVLink exchange + merge (the sharded path's replacement for all-gather + slm_merge_top2 when the gather buffers are
+ * peer-mapped, e.g. torch symmetric memory over NVLink / NVSwitch).
+ *   peer_keys_host[r]  : device address, valid on THIS GPU, of rank r's key buffer: 2 * world * nq_capacity * 16 bytes
+ *                        (layout [2][world][nq_capacity][2] keys; 64-bit keys, or 32-bit compact keys
+ *                        (distance << 16 | index) in the front half when nt_global <= 65536 -- config 4's vocabulary)
  *   peer_flags_host[r] : device address of rank r's flag array uint32[2][world] (zero-initialised once)
- * The kernel stores this rank's nq x 2 keys into slot [step & 1][rank] of every peer's buffer (16-byte stores
- * over NVLink), publishes `step` into every peer's flag [step & 1][rank] with a system-scope release, waits
- * (bounded) until its own flags show `step` from every rank, then merges and finalises like slm_merge_top2.
- * `step` must be the same on all ranks, start at 1 and increase by 1 per call; two buffer halves make the
- * scheme safe without any other synchronisation.  nq <= 8192 and nq <= nq_capacity.
+ *   nt_global          : number of train rows over ALL ranks (selects the key width; must be the same on every rank;
+ *                        0 = unknown, 64-bit keys)
+ * A producer kernel stores this rank's nq x 2 keys into slot [step & 1][rank] of every peer's buffer (16- / 8-byte
+ * stores over NVLink) and publishes `step` into every peer's flag [step & 1][rank] with a system-scope release; a
+ * second kernel (programmatic dependent launch: resident while the producer drains) polls this rank's own flags
+ * until every rank shows `step`, then merges and finalises like slm_merge_top2.  `step` must be the same on all
+ * ranks, start at 1 and increase by 1 per call; two buffer halves make the scheme safe without any other
+ * synchronisation.  nq <= nq_capacity (any size).  A peer that never delivers is reported, not waited for forever:
+ * the merge kernel gives up after a bounded number of polls, leaves the outputs untouched, and the NEXT exchange call
+ * (or slm_exchange_status) on this ctx returns SLM_ERR_TIMEOUT naming the rank and step.
  */
-int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys_dev, int64_t nq, int64_t nq_capacity,
+int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys_dev, int64_t nq, int64_t nq_capacity, int64_t nt_global,
                        const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank, int32_t world,
                        uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out_dev,
                        int32_t *dist_out_dev, uint8_t *accept_out_dev, void *stream);
 
 /*
  * The whole sharded step in one call: search this rank's train block, exchange over NVLink, merge, finalise.
- * Arguments as slm_knn2_keys + slm_exchange_merge.  With the tensor variant the refine kernel stores each query's
- * keys straight into the peers' buffers and its last block publishes the flags, waits and merges -- no
- * separate exchange kernel; other variants run the search followed by slm_exchange_merge.
+ * Arguments as slm_knn2_keys + slm_exchange_merge.  With the tensor variants the refine kernel is the producer (every
+ * query's exact keys go straight into the peers' buffers); other variants run the search followed by a store kernel.
  */
 int slm_knn2_exchange(slm_ctx *ctx, const uint32_t *q_dev, int64_t nq, const uint32_t *t_dev, int64_t nt,
-                      int64_t train_index_base, int64_t nq_capacity, const uint64_t *peer_keys_host,
+                      int64_t train_index_base, int64_t nq_capacity, int64_t nt_global, const uint64_t *peer_keys_host,
                       const uint64_t *peer_flags_host, int32_t rank, int32_t world, uint32_t step, int32_t ratio_num,
                       int32_t ratio_den, int32_t *idx_out_dev, int32_t *dist_out_dev, uint8_t *accept_out_dev,
                       void *stream);
+/* SLM_OK, or SLM_ERR_TIMEOUT if an earlier exchange on this ctx lost a peer (clears the report).  Call after the
+ * stream has been synchronised. */
+int slm_exchange_status(slm_ctx *ctx);
+
+/*
+ * Point3D.find_2D_and_3D_correspondenses' extra condition (Point3D.py:45-46): accept_dev[i] &= |X|, |Y|, |Z| <
+ * max_distance of query i's triangulated point, pts3d_dev = float64[nq][3].  Run between slm_knn2_filter and
+ * slm_compact_matches; the gathers of Point3D.py:50-52 are slm_gather_rows.
+ */
+int slm_filter_points3d(slm_ctx *ctx, const double *pts3d_dev, int64_t nq, double max_distance, uint8_t *accept_dev,
+                        void *stream);
+
+/*
+ * In-process ceilings of the pipes the distance kernels run on (bench.py's roofline denominators; synchronous).
+ * slm_probe_tensor_peak: back-to-back tcgen05.mma on every SM from shared memory; kind 0 = kind::f8f6f4 (variant
+ *   TENSOR), 1 = kind::mxf4.block_scale (variant TENSOR4).  `loops` jobs per CTA, best of `reps` launches.
+ *   tflops_out = dense TFLOP/s (2 flop per MAC), mac_per_clk_per_sm_out from clock64 inside the kernel.
+ * slm_probe_popc_peak: the inner loop of variant POPC (8 XOR + 8 POPC + top-2 update per comparison) on every SM.
+ */
+int slm_probe_tensor_peak(slm_ctx *ctx, int32_t kind, int32_t loops, int32_t reps, double *tflops_out,
+                          double *mac_per_clk_per_sm_out);
+int slm_probe_popc_peak(slm_ctx *ctx, int32_t reps, double *tcmp_per_s_out, double *popc_lanes_per_clk_per_sm_out);
 
 /*
  * Device-side compaction of accepted rows (the gathers at tracking.py:32-33 start from this list):
@@ -194,6 +226,7 @@ int slm_gather_rows(slm_ctx *ctx, const void *src_dev, int32_t row_bytes, const 
  * slm_chi2_scan: dist_out_dev[i] = sum_w 2*(h[w]-db[i][w])^2 / max(1, h[w]+db[i][w]) in float64 for the n_db stored
  *   histograms db_dev int32[n_db][n_words], bit-exact with numpy (same division, same pairwise summation
  *   order), plus best_idx_dev / best_val_dev = (np.argmin, np.min) -- first minimum wins.
+ *   n_words <= 12288: the query histogram is staged in 48 KB of shared memory (larger vocabularies: SLM_ERR_INVALID).
  */
 int slm_bow_hist(slm_ctx *ctx, const int32_t *words_dev, int64_t n, int32_t stride, int32_t n_words,
                  int32_t *hist_out_dev, void *stream);

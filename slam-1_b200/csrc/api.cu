@@ -27,22 +27,49 @@ int slm_fail(int code, const char *fmt, ...)
 
 int slm_buf_reserve(slm_ctx *ctx, slm_buf *buf, size_t bytes)
 {
-    (void)ctx;
     if (bytes <= buf->bytes) return SLM_OK;
-    size_t want = bytes + bytes / 4 + 4096;  // slack so that slowly growing inputs do not realloc each call
+    const size_t want = bytes + bytes / 4 + 4096;  // slack so that slowly growing inputs do not realloc each call
+    // Stream-ordered growth: the old block is released after everything already queued on the call's stream (slm_enter
+    // has ordered that stream behind the previous call's), the new one is usable by everything queued after this point.
+    // No device-wide synchronisation, no host stall in the middle of a stream of calls.
+    cudaStream_t s = ctx->cur_stream;
     if (buf->p) {
-        SLM_CUDA(cudaDeviceSynchronize());
-        SLM_CUDA(cudaFree(buf->p));
+        SLM_CUDA(cudaFreeAsync(buf->p, s));
         buf->p = nullptr;
         buf->bytes = 0;
     }
-    cudaError_t e = cudaMalloc(&buf->p, want);
+    cudaError_t e = cudaMallocAsync(&buf->p, want, s);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         buf->p = nullptr;
-        return slm_fail(SLM_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return slm_fail(SLM_ERR_NOMEM, "cudaMallocAsync(%zu) failed: %s", want, cudaGetErrorString(e));
     }
     buf->bytes = want;
+    return SLM_OK;
+}
+
+int slm_enter(slm_ctx *ctx, cudaStream_t stream)
+{
+    // The workspace of a ctx is shared by all its calls.  A call on another stream than the previous one first waits,
+    // on the device, for everything queued on that stream so far (which includes the previous call's kernels).
+    if (ctx->have_last && ctx->last_stream != stream) {
+        cudaError_t e = cudaEventRecord(ctx->last_ev, ctx->last_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, ctx->last_ev, 0);
+        if (e != cudaSuccess) {                     // e.g. the caller destroyed the previous stream
+            (void)cudaGetLastError();
+            SLM_CUDA(cudaDeviceSynchronize());
+        }
+    }
+    ctx->cur_stream = stream;
+    ctx->last_stream = stream;
+    ctx->have_last = true;
+    return SLM_OK;
+}
+
+int slm_leave(slm_ctx *ctx, cudaStream_t stream)
+{
+    (void)stream;
+    (void)ctx;
     return SLM_OK;
 }
 
@@ -68,7 +95,11 @@ static int pin_reserve(slm_ctx *ctx, size_t bytes)
 
 int slm_prof_mark(slm_ctx *ctx, cudaStream_t stream, int tag)
 {
-    if (!ctx->profile || ctx->prof_n >= slm_ctx::kMaxProf) return SLM_OK;
+    if (!ctx->profile) return SLM_OK;
+    if (ctx->prof_n >= slm_ctx::kMaxProf) {       // full: count what is lost, slm_profile_read reports it
+        ctx->prof_dropped += 1;
+        return SLM_OK;
+    }
     if (!ctx->prof_ev) {
         ctx->prof_ev = new (std::nothrow) cudaEvent_t[slm_ctx::kMaxProf];
         ctx->prof_tag = new (std::nothrow) unsigned char[slm_ctx::kMaxProf];
@@ -120,7 +151,9 @@ static int knn2_keys_dispatch(slm_ctx *ctx, const uint32_t *q, int64_t nq, const
         return slm_fail(SLM_ERR_INVALID, "descriptor pointers must be 16-byte aligned");
     switch (ctx->variant) {
     case SLM_VARIANT_TENSOR:
-        return slm_tc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
+        return slm_tc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream, false);
+    case SLM_VARIANT_TENSOR4:
+        return slm_tc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream, true);
     case SLM_VARIANT_BMMA:
         return slm_bmma_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
     case SLM_VARIANT_POPC:
@@ -166,6 +199,22 @@ int slm_create(int device, slm_ctx **ctx_out)
     }
     ctx->no_frame_refine = getenv("SLM_TC_NO_FRAME_REFINE") != nullptr;
     ctx->tc_plan_mt = getenv("SLM_TC_PLAN_MT") != nullptr;
+    if (const char *e = getenv("SLM_TC_FP4")) ctx->tc_fp4 = atoi(e) != 0;
+    if (const char *e = getenv("SLM_TC4_CHUNK")) {
+        int v = atoi(e);
+        if (v == 120 || v == 40) ctx->tc4_chunk = v;
+    }
+    ctx->no_pdl = getenv("SLM_NO_PDL") != nullptr;
+    ctx->exchange_max_blocks = 2ll * prop.multiProcessorCount;
+    if (const char *e = getenv("SLM_EXCHANGE_MAX_BLOCKS")) {
+        long long v = atoll(e);
+        if (v >= 1) ctx->exchange_max_blocks = v;
+    }
+    if (const char *e = getenv("SLM_EXCHANGE_MAX_POLLS")) {
+        long long v = atoll(e);
+        if (v >= 1 && v <= 0xFFFFFFFFll) ctx->exchange_max_polls = (unsigned)v;
+    }
+    ctx->exchange_wide_keys = getenv("SLM_EXCHANGE_WIDE_KEYS") != nullptr;
     if (const char *e = getenv("SLM_TC_CHAIN")) ctx->tc_chain_max = atoi(e);
     if (const char *e = getenv("SLM_TC_CHAIN_MIN")) ctx->tc_chain_min = atoi(e);
     if (const char *e = getenv("SLM_FRAME_MAX_CLK")) ctx->frame_max_clk = atoll(e);
@@ -180,6 +229,7 @@ int slm_create(int device, slm_ctx **ctx_out)
     SLM_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming));
+    SLM_CUDA(cudaEventCreateWithFlags(&ctx->last_ev, cudaEventDisableTiming));
     *ctx_out = ctx;
     return SLM_OK;
 }
@@ -194,6 +244,8 @@ int slm_destroy(slm_ctx *ctx)
         if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->done_counter) cudaFree(ctx->done_counter);
+    if (ctx->exchange_status) cudaFreeHost(ctx->exchange_status);
+    if (ctx->last_ev) cudaEventDestroy(ctx->last_ev);
     if (ctx->prof_ev) {
         for (int i = 0; i < slm_ctx::kMaxProf; ++i) cudaEventDestroy(ctx->prof_ev[i]);
         delete[] ctx->prof_ev;
@@ -213,7 +265,7 @@ int slm_destroy(slm_ctx *ctx)
 int slm_set_variant(slm_ctx *ctx, int variant)
 {
     if (!ctx) return slm_fail(SLM_ERR_INVALID, "ctx is NULL");
-    if (variant < SLM_VARIANT_AUTO || variant > SLM_VARIANT_BMMA)
+    if (variant < SLM_VARIANT_AUTO || variant > SLM_VARIANT_TENSOR4)
         return slm_fail(SLM_ERR_INVALID, "unknown variant %d", variant);
     ctx->variant = variant;
     return SLM_OK;
@@ -253,6 +305,12 @@ int slm_profile_read(slm_ctx *ctx, double *kernel_ms_out, int64_t *launches_out)
     if (kernel_ms_out) *kernel_ms_out = total;
     if (launches_out) *launches_out = launches;
     ctx->prof_n = 0;
+    if (ctx->prof_dropped > 0) {
+        const long long d = ctx->prof_dropped;
+        ctx->prof_dropped = 0;
+        return slm_fail(SLM_ERR_UNSUPPORTED, "profile buffer overflowed: %lld event marks were dropped (read at least every %d marks)",
+                        d, slm_ctx::kMaxProf);
+    }
     return SLM_OK;
 }
 
@@ -263,6 +321,7 @@ int slm_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t
     SLM_TRY(check_sizes(nq, nt, base));
     if (nq == 0) return SLM_OK;
     if (!q || !keys_out || (nt > 0 && !t)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(slm_enter(ctx, (cudaStream_t)stream));
     SLM_TRY(slm_prof_mark(ctx, (cudaStream_t)stream, SLM_TAG_CALL_BEGIN));
     SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys_out, (cudaStream_t)stream));
     return slm_prof_mark(ctx, (cudaStream_t)stream, SLM_TAG_CALL_END);
@@ -278,6 +337,7 @@ int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t 
     if (nq == 0) return SLM_OK;
     if (!q || (nt > 0 && !t)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
     cudaStream_t stream = (cudaStream_t)stream_;
+    SLM_TRY(slm_enter(ctx, stream));
     const bool cross = cross_check && accept_out && nt > 0;
     if (ctx->variant == SLM_VARIANT_AUTO && nt > 0 && slm_frame_eligible(ctx, nq, nt, cross)) {
         // frame-to-frame shapes: search, merge, ratio and cross-check in one launch
@@ -345,7 +405,9 @@ int slm_knn2_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_frames, int64
         if (pairs_host[i] < 0 || pairs_host[i] >= n_frames)
             return slm_fail(SLM_ERR_INVALID, "pair %lld references frame %d outside [0,%lld)", (long long)(i / 2),
                             pairs_host[i], (long long)n_frames);
+    if ((uintptr_t)desc & 15) return slm_fail(SLM_ERR_INVALID, "descriptor pointers must be 16-byte aligned");
     cudaStream_t stream = (cudaStream_t)stream_;
+    SLM_TRY(slm_enter(ctx, stream));
     const int64_t rows = n_pairs * n_per_frame;
     SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)rows * 16));
     // Chain plan (tensor variant): pairs sorted by query frame, cut into units of <= L pairs that share it, longest
@@ -408,69 +470,93 @@ int slm_merge_top2(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards, int
     if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
     if (nq == 0) return SLM_OK;
     if (!gathered) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(slm_enter(ctx, (cudaStream_t)stream_));
     SLM_TRY(slm_prof_mark(ctx, (cudaStream_t)stream_, SLM_TAG_CALL_BEGIN));
     SLM_TRY(slm_merge_finalize(ctx, gathered, n_shards, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out,
                                (cudaStream_t)stream_));
     return slm_prof_mark(ctx, (cudaStream_t)stream_, SLM_TAG_CALL_END);
 }
 
-int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys, int64_t nq, int64_t nq_capacity,
-                       const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank, int32_t world,
-                       uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out, int32_t *dist_out,
-                       uint8_t *accept_out, void *stream)
+static int check_exchange_args(int64_t nq, int64_t nq_capacity, int64_t nt_global, const uint64_t *peer_keys_host,
+                               const uint64_t *peer_flags_host, int32_t rank, int32_t world, uint32_t step, int32_t ratio_num,
+                               int32_t ratio_den)
 {
-    SLM_TRY(check_ctx(ctx));
-    if (world < 1 || world > 16 || rank < 0 || rank >= world) return slm_fail(SLM_ERR_INVALID, "bad rank/world (%d/%d)", rank, world);
-    if (nq < 0 || nq > 8192 || nq > nq_capacity) return slm_fail(SLM_ERR_INVALID, "nq must be <= min(8192, nq_capacity)");
+    if (world < 1 || world > kSlmMaxWorld || rank < 0 || rank >= world)
+        return slm_fail(SLM_ERR_INVALID, "bad rank/world (%d/%d; at most %d ranks)", rank, world, kSlmMaxWorld);
+    if (nq < 1 || nq > nq_capacity) return slm_fail(SLM_ERR_INVALID, "nq must be in 1..nq_capacity (nq=%lld capacity=%lld)",
+                                                    (long long)nq, (long long)nq_capacity);
+    if (nt_global < 0) return slm_fail(SLM_ERR_INVALID, "nt_global must be >= 0");
     if (step == 0) return slm_fail(SLM_ERR_INVALID, "step starts at 1");
     if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
-    if (!peer_keys_host || !peer_flags_host || (nq > 0 && !local_keys)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
-    SLM_TRY(slm_prof_mark(ctx, (cudaStream_t)stream, SLM_TAG_CALL_BEGIN));
-    SLM_TRY(slm_exchange_merge_impl(ctx, local_keys, nq, nq_capacity, peer_keys_host, peer_flags_host, rank, world, step,
-                                    ratio_num, ratio_den, idx_out, dist_out, accept_out, (cudaStream_t)stream));
-    return slm_prof_mark(ctx, (cudaStream_t)stream, SLM_TAG_CALL_END);
+    if (!peer_keys_host || !peer_flags_host) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    return SLM_OK;
+}
+
+int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys, int64_t nq, int64_t nq_capacity, int64_t nt_global,
+                       const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank, int32_t world,
+                       uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out, int32_t *dist_out,
+                       uint8_t *accept_out, void *stream_)
+{
+    SLM_TRY(check_ctx(ctx));
+    SLM_TRY(slm_exchange_check(ctx));
+    SLM_TRY(check_exchange_args(nq, nq_capacity, nt_global, peer_keys_host, peer_flags_host, rank, world, step, ratio_num, ratio_den));
+    if (!local_keys) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SLM_TRY(slm_enter(ctx, stream));
+    SLM_TRY(slm_prof_mark(ctx, stream, SLM_TAG_CALL_BEGIN));
+    slm_exchange ex;
+    SLM_TRY(slm_exchange_setup(ctx, &ex, peer_keys_host, peer_flags_host, rank, world, step, nq_capacity, nt_global));
+    SLM_TRY(slm_exchange_store(ctx, ex, local_keys, nq, stream));
+    SLM_TRY(slm_exchange_wait_merge(ctx, ex, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out, stream));
+    return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
 }
 
 int slm_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
-                      int64_t nq_capacity, const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank,
-                      int32_t world, uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out,
+                      int64_t nq_capacity, int64_t nt_global, const uint64_t *peer_keys_host, const uint64_t *peer_flags_host,
+                      int32_t rank, int32_t world, uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out,
                       int32_t *dist_out, uint8_t *accept_out, void *stream_)
 {
     SLM_TRY(check_ctx(ctx));
+    SLM_TRY(slm_exchange_check(ctx));
     SLM_TRY(check_sizes(nq, nt, base));
-    if (world < 1 || world > kSlmMaxWorld || rank < 0 || rank >= world)
-        return slm_fail(SLM_ERR_INVALID, "bad rank/world (%d/%d)", rank, world);
-    if (nq < 1 || nq > 8192 || nq > nq_capacity) return slm_fail(SLM_ERR_INVALID, "nq must be in 1..min(8192, nq_capacity)");
-    if (step == 0) return slm_fail(SLM_ERR_INVALID, "step starts at 1");
-    if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
-    if (!q || (nt > 0 && !t) || !peer_keys_host || !peer_flags_host) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(check_exchange_args(nq, nq_capacity, nt_global, peer_keys_host, peer_flags_host, rank, world, step, ratio_num, ratio_den));
+    if (nt_global > 0 && base + nt > nt_global) return slm_fail(SLM_ERR_INVALID, "train_index_base + nt exceeds nt_global");
+    if (!q || (nt > 0 && !t)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
     cudaStream_t stream = (cudaStream_t)stream_;
-    const bool tensor = nt > 0 && (ctx->variant == SLM_VARIANT_TENSOR ||
+    SLM_TRY(slm_enter(ctx, stream));
+    const bool tensor = nt > 0 && (ctx->variant == SLM_VARIANT_TENSOR || ctx->variant == SLM_VARIANT_TENSOR4 ||
                                    (ctx->variant == SLM_VARIANT_AUTO && nq > 8 && nq * nt >= (1ll << 18)));
     SLM_TRY(slm_prof_mark(ctx, stream, SLM_TAG_CALL_BEGIN));
+    slm_exchange ex;
+    SLM_TRY(slm_exchange_setup(ctx, &ex, peer_keys_host, peer_flags_host, rank, world, step, nq_capacity, nt_global));
     if (tensor) {
-        if (!ctx->done_counter) {
-            SLM_CUDA(cudaMalloc(&ctx->done_counter, sizeof(unsigned)));
-            SLM_CUDA(cudaMemset(ctx->done_counter, 0, sizeof(unsigned)));
-        }
-        slm_exchange ex{};
-        for (int r = 0; r < world; ++r) {
-            ex.peer_keys[r] = reinterpret_cast<unsigned long long *>(peer_keys_host[r]);
-            ex.peer_flags[r] = reinterpret_cast<unsigned *>(peer_flags_host[r]);
-        }
-        ex.rank = rank; ex.world = world; ex.step = step; ex.cap = nq_capacity;
-        ex.ratio_num = ratio_num; ex.ratio_den = ratio_den;
-        ex.idx_out = idx_out; ex.dist_out = dist_out; ex.accept_out = accept_out;
-        ex.done_counter = ctx->done_counter;
-        SLM_TRY(slm_tc_knn2_exchange(ctx, q, nq, t, nt, base, ex, stream));
+        // the refine kernel is the producer: every query's exact keys go straight into the peers' buffers
+        const bool fp4 = ctx->variant == SLM_VARIANT_TENSOR4 || (ctx->variant == SLM_VARIANT_AUTO && ctx->tc_fp4);
+        SLM_TRY(slm_tc_knn2_exchange(ctx, q, nq, t, nt, base, ex, stream, fp4));
     } else {
         SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)nq * 16));
         uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
         SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys, stream));
-        SLM_TRY(slm_exchange_merge_impl(ctx, keys, nq, nq_capacity, peer_keys_host, peer_flags_host, rank, world, step,
-                                        ratio_num, ratio_den, idx_out, dist_out, accept_out, stream));
+        SLM_TRY(slm_exchange_store(ctx, ex, keys, nq, stream));
     }
+    SLM_TRY(slm_exchange_wait_merge(ctx, ex, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out, stream));
     return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
+}
+
+int slm_exchange_status(slm_ctx *ctx)
+{
+    if (!ctx) return slm_fail(SLM_ERR_INVALID, "ctx is NULL");
+    return slm_exchange_check(ctx);
+}
+
+int slm_filter_points3d(slm_ctx *ctx, const double *pts3d, int64_t nq, double max_distance, uint8_t *accept, void *stream)
+{
+    SLM_TRY(check_ctx(ctx));
+    if (nq < 0) return slm_fail(SLM_ERR_INVALID, "negative size");
+    if (nq == 0) return SLM_OK;
+    if (!pts3d || !accept) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(slm_enter(ctx, (cudaStream_t)stream));
+    return slm_filter_points3d_impl(ctx, pts3d, nq, max_distance, accept, (cudaStream_t)stream);
 }
 
 int slm_compact_matches(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
@@ -480,6 +566,7 @@ int slm_compact_matches(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, c
     if (nq < 0) return slm_fail(SLM_ERR_INVALID, "negative size");
     if (!count_out || (nq > 0 && (!idx || !dist || !accept || !matches_out)))
         return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(slm_enter(ctx, (cudaStream_t)stream));
     return slm_compact(ctx, idx, dist, accept, nq, stop_at_short_row, matches_out, count_out, (cudaStream_t)stream);
 }
 
@@ -492,6 +579,7 @@ int slm_gather_rows(slm_ctx *ctx, const void *src, int32_t row_bytes, const int3
     if (capacity < 0) return slm_fail(SLM_ERR_INVALID, "negative capacity");
     if (capacity == 0) return SLM_OK;
     if (!src || !matches || !count || !out) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(slm_enter(ctx, (cudaStream_t)stream));
     return slm_gather(ctx, src, row_bytes, matches, count, capacity, column, out, (cudaStream_t)stream);
 }
 
@@ -502,6 +590,7 @@ int slm_bow_hist(slm_ctx *ctx, const int32_t *words, int64_t n, int32_t stride, 
     if (n < 0 || stride < 1 || n_words < 1) return slm_fail(SLM_ERR_INVALID, "bad size (n=%lld stride=%d n_words=%d)",
                                                               (long long)n, stride, n_words);
     if (!hist_out || (n > 0 && !words)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(slm_enter(ctx, (cudaStream_t)stream));
     return slm_bow_hist_impl(ctx, words, n, stride, n_words, hist_out, (cudaStream_t)stream);
 }
 
@@ -513,6 +602,7 @@ int slm_chi2_scan(slm_ctx *ctx, const int32_t *hist, const int32_t *db, int64_t 
                                                                       (long long)n_db, n_words);
     if (n_db == 0) return SLM_OK;
     if (!hist || !db || !dist_out || !best_idx || !best_val) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(slm_enter(ctx, (cudaStream_t)stream));
     return slm_chi2_scan_impl(ctx, hist, db, n_db, n_words, dist_out, best_idx, best_val, (cudaStream_t)stream);
 }
 
@@ -523,6 +613,7 @@ int slm_vocab_update(slm_ctx *ctx, const uint32_t *desc, int64_t n, const int32_
     if (n < 0 || n > 0x7FFFFFFFll || stride < 1 || n_words < 1)
         return slm_fail(SLM_ERR_INVALID, "bad size (n=%lld stride=%d n_words=%d)", (long long)n, stride, n_words);
     if (!vocab || (n > 0 && (!desc || !words))) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    SLM_TRY(slm_enter(ctx, (cudaStream_t)stream));
     return slm_vocab_update_impl(ctx, desc, n, words, stride, vocab, n_words, counts_out, changed_out, (cudaStream_t)stream);
 }
 
@@ -536,6 +627,7 @@ int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t
     if (nq == 0) return SLM_OK;
     if (!q_host || (nt > 0 && !t_host)) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
     cudaStream_t s = ctx->own_stream;
+    SLM_TRY(slm_enter(ctx, s));
     // device layout: [q | t | idx | dist | accept], every block 256-byte aligned
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t q_b = up((size_t)nq * 32), t_b = up((size_t)nt * 32), i_b = up((size_t)nq * 8), a_b = up((size_t)nq);

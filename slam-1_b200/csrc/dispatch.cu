@@ -14,7 +14,7 @@ int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
         return slm_frame_knn2(ctx, q, nq, t, nt, base, 0, 1, 0, keys_out, nullptr, nullptr, nullptr, stream);
     if (nq <= 8) return slm_stream_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
     if (nq * nt < kAutoTensorMinCmp) return slm_popc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
-    return slm_tc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream);
+    return slm_tc_knn2_keys(ctx, q, nq, t, nt, base, keys_out, stream, ctx->tc_fp4 != 0);
 }
 
 int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,

@@ -88,68 +88,14 @@ __global__ void merge_finalize_kernel(const unsigned long long *gathered, int n_
         accept_out[i] = (ratio_num > 0 ? (has1 && has2 && (long long)ratio_den * d1 < (long long)ratio_num * d2) : has1) ? 1 : 0;
 }
 
-// ---- NVLink exchange fused with the merge (sharded path) -------------------------------------------------
-constexpr int kMaxWorld = 16;
-struct ExchangeParams {
-    unsigned long long *peer_keys[kMaxWorld];   // every rank's buffer uint64[2][world][cap][2], mapped on this GPU
-    unsigned *peer_flags[kMaxWorld];            // every rank's flags uint32[2][world]
-    int rank, world;
-    unsigned step;
-    long long nq, cap;
-};
-
-__global__ void __launch_bounds__(1024) exchange_merge_kernel(ExchangeParams p, const unsigned long long *local_keys,
-                                                              int ratio_num, int ratio_den, int *idx_out, int *dist_out,
-                                                              unsigned char *accept_out)
+// Point3D.find_2D_and_3D_correspondenses (Point3D.py:45-46): a match is kept only if the query's triangulated point has
+// |X|, |Y|, |Z| < max_Distance (strict, float64 like the reference's numpy array).
+__global__ void filter_points3d_kernel(const double *pts, long long n, double max_distance, unsigned char *accept)
 {
-    const int tid = threadIdx.x;
-    const unsigned parity = p.step & 1u;
-    // 1. push this rank's keys into slot [parity][rank] of every peer's buffer (peer stores ride NVLink)
-    for (long long i = tid; i < p.nq; i += blockDim.x) {
-        const ulonglong2 k = reinterpret_cast<const ulonglong2 *>(local_keys)[i];
-        for (int r = 0; r < p.world; ++r) {
-            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(p.peer_keys[r]) + ((long long)parity * p.world + p.rank) * p.cap + i;
-            *dst = k;
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    // 2. publish, 3. wait for everybody's keys of this step (bounded: a lost peer traps instead of hanging)
-    if (tid < p.world) {
-        unsigned *flag = p.peer_flags[tid] + parity * p.world + p.rank;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(p.step) : "memory");
-        const unsigned *mine = p.peer_flags[p.rank] + parity * p.world + tid;
-        unsigned v, spins = 0;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-            if (++spins > (1u << 27)) {
-                printf("slammatch: exchange flag of rank %d never reached step %u (have %u)\n", tid, p.step, v);
-                __trap();
-            }
-        } while ((int)(v - p.step) < 0);
-    }
-    __syncthreads();
-    // 4. merge the world's top-2 lists from the local buffer and finalise
-    const unsigned long long *g = p.peer_keys[p.rank] + (long long)parity * p.world * p.cap * 2;
-    for (long long i = tid; i < p.nq; i += blockDim.x) {
-        unsigned long long k1 = kKeyNone, k2 = kKeyNone;
-        for (int r = 0; r < p.world; ++r) {
-            const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(g)[(long long)r * p.cap + i];
-            unsigned long long m = max(k1, v.x);
-            k1 = min(k1, v.x);
-            k2 = min(k2, m);
-            m = max(k1, v.y);
-            k1 = min(k1, v.y);
-            k2 = min(k2, m);
-        }
-        const bool has1 = k1 != kKeyNone, has2 = k2 != kKeyNone;
-        const int i1 = has1 ? (int)(k1 & 0xFFFFFFFFull) : -1, d1 = has1 ? (int)(k1 >> 32) : -1;
-        const int i2 = has2 ? (int)(k2 & 0xFFFFFFFFull) : -1, d2 = has2 ? (int)(k2 >> 32) : -1;
-        if (idx_out) reinterpret_cast<int2 *>(idx_out)[i] = make_int2(i1, i2);
-        if (dist_out) reinterpret_cast<int2 *>(dist_out)[i] = make_int2(d1, d2);
-        if (accept_out)
-            accept_out[i] = (ratio_num > 0 ? (has1 && has2 && (long long)ratio_den * d1 < (long long)ratio_num * d2) : has1) ? 1 : 0;
-    }
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !accept[i]) return;
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    if (!(fabs(x) < max_distance && fabs(y) < max_distance && fabs(z) < max_distance)) accept[i] = 0;
 }
 
 // Ordered compaction by one CTA: block-wide exclusive scan over 1024-row chunks.
@@ -285,19 +231,10 @@ int slm_merge_finalize(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards,
     return SLM_OK;
 }
 
-int slm_exchange_merge_impl(slm_ctx *ctx, const uint64_t *local_keys, int64_t nq, int64_t cap,
-                            const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank, int32_t world,
-                            uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out, int32_t *dist_out,
-                            uint8_t *accept_out, cudaStream_t stream)
+int slm_filter_points3d_impl(slm_ctx *ctx, const double *pts3d, int64_t n, double max_distance, uint8_t *accept,
+                             cudaStream_t stream)
 {
-    ExchangeParams p{};
-    for (int r = 0; r < world; ++r) {
-        p.peer_keys[r] = reinterpret_cast<unsigned long long *>(peer_keys_host[r]);
-        p.peer_flags[r] = reinterpret_cast<unsigned *>(peer_flags_host[r]);
-    }
-    p.rank = rank; p.world = world; p.step = step; p.nq = nq; p.cap = cap;
-    exchange_merge_kernel<<<1, 1024, 0, stream>>>(p, reinterpret_cast<const unsigned long long *>(local_keys), ratio_num,
-                                                  ratio_den, idx_out, dist_out, accept_out);
+    filter_points3d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pts3d, n, max_distance, accept);
     SLM_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return SLM_OK;

@@ -27,12 +27,16 @@
 // re-scores just those candidate rows with XOR+POPC and applies the reference tie-break bit-exactly.
 // Cost per element: ~0.5 FMNMX3; data-independent (no divergence on adversarial inputs).
 #include <cfloat>
+#include <atomic>
 #include "slm_internal.cuh"
+#include "exchange.cuh"
 #include "tc_common.cuh"
+#include "tc_params.cuh"
 
 namespace {
 
-constexpr int kTileM = 128;
+using namespace tcp;
+
 constexpr int kTileN = 256;
 constexpr int kChunk = 32;
 constexpr int kChunksPerTile = kTileN / kChunk;   // 8
@@ -44,34 +48,7 @@ constexpr int kExpThreads = kExpWarps * 32;        // 256
 constexpr int kThreads = kEpiThreads + kExpThreads + 32;   // 544
 constexpr uint32_t kATileBytes = kTileM * 256;     // 32 KB
 constexpr uint32_t kBTileBytes = kTileN * 256;     // 64 KB
-constexpr int kChunkBits = 15;                     // chunk counter bits in the packed fp32 key
-constexpr int kChunkMask = (1 << kChunkBits) - 1;  // 32767
 constexpr int kMaxEpochTiles = (1 << kChunkBits) / kChunksPerTile;   // 4096 tiles per candidate epoch
-constexpr float kKeyScale = (float)(1 << kChunkBits);
-constexpr int kKeyBias = 256 << kChunkBits;        // makes (int)key non-negative: |dot| <= 256
-
-struct TcParams {
-    const uint32_t *q, *t;        // single problem
-    const uint32_t *desc;         // batched: uint32[n_frames][n_per_frame][8] (else nullptr)
-    const int32_t *pairs;         // batched: device int32[n_prob][2]
-    long long frame_words;
-    int nq, nt;
-    int n_prob;
-    int mt;                       // query tiles per group (1..kMaxMT)
-    int n_groups;                 // ceil(nq / (128 * mt))
-    int range_tiles, n_ranges;    // the train set is cut into n_ranges ranges of range_tiles 256-row tiles
-    int cpg;                      // CTAs (1-CTA kernel) / clusters (2-CTA kernel) per query group (pair):
-                                  // unit c walks ranges c, c + cpg, c + 2 cpg, ... of its group
-    int chunk;                    // candidate chunk width in train rows: 32, or 16 in chained batches (refine kernels)
-    int rpe, n_epochs;            // ranges per candidate epoch (rpe * range_tiles <= 4096 tiles), epochs per unit
-    float2 *cand;                 // [n_prob][nq][cpg * n_epochs][2 sets]: best two chunk keys per epilogue set
-    // Chained batches (2-CTA kernel, config 3): grid.y indexes UNITS = runs of pairs that share the query frame.  The
-    // cluster expands that frame's query tiles once and walks the train frames of the run back to back (one
-    // candidate flush per pair), instead of paying the cluster start-up once per pair.
-    const int32_t *chain_pairs;   // device int32[n_prob][2], pairs sorted by query frame (nullptr = not chained)
-    const int32_t *chain_prob;    // device int32[n_prob]: caller's pair index of every sorted pair (output slot)
-    const int32_t *chain_units;   // device int32[n_units][2] = (first sorted pair, number of pairs)
-};
 
 struct TcBarriers {
     uint64_t a_full;
@@ -607,20 +584,54 @@ __device__ __forceinline__ void top2_insert_max(unsigned long long &k1, unsigned
     k2 = max(k2, m);
 }
 
+// Candidate key -> (dot + 257) << 32 | ~global chunk, so that a 64-bit max prefers the larger dot and, on ties,
+// the chunk with the lower global index.  Undoes the unit's strided range walk: the key carries the chunk counter
+// inside the unit's candidate epoch.
+__device__ __forceinline__ unsigned long long cand_to_chunk_key(const TcParams &p, float key, int slot)
+{
+    const int ki = (int)key + kKeyBias;
+    const int lc = kChunkMask - (ki & kChunkMask);
+    const int unit = slot / p.n_epochs, epoch = slot % p.n_epochs;
+    const int cpt = p.tile_n / p.chunk;                       // chunks per tile
+    const int lt = lc / cpt;                                  // tile counter inside the epoch
+    const int range = unit + (epoch * p.rpe + lt / p.range_tiles) * p.cpg;
+    const unsigned gchunk = (unsigned)((range * p.range_tiles + lt % p.range_tiles) * cpt + lc % cpt);
+    return ((unsigned long long)((ki >> kChunkBits) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk);
+}
+
+// Exact distance of one row pair (XOR + POPC), the arithmetic of the reference's matcher.
+__device__ __forceinline__ unsigned hamming256(const uint4 &qa, const uint4 &qb, const uint4 &ta, const uint4 &tb)
+{
+    return __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+           __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+}
+
+// Exact key of a candidate row inside the two winning chunks: (distance << 8) | (chunk selector << 7) | position, so a
+// 32-bit min is the (distance, global index) order -- the reference tie-break -- as long as the lower-index chunk has
+// selector 0.  Chunks hold at most 128 rows.
+__device__ __forceinline__ unsigned refine_key(unsigned d, int sel, int pos) { return (d << 8) | ((unsigned)sel << 7) | (unsigned)pos; }
+__device__ __forceinline__ unsigned long long refine_widen(unsigned k, unsigned glo, unsigned ghi, int chunk, long long base)
+{
+    if (k == 0xFFFFFFFFu) return kKeyNone;
+    const long long row = (long long)((k & 128u) ? ghi : glo) * chunk + (k & 127u);
+    return ((unsigned long long)(k >> 8) << 32) | (unsigned long long)(base + row);
+}
+
 // G lanes per (problem, query); 32 / G queries per warp.
 //   phase 1: reduce the query's candidate chunk keys (2 per epilogue set per range) to the best two chunks of
 //            the whole train set by (max dot desc, global chunk index asc).  The exact top-2 rows lie inside
 //            them: the nearest row's chunk has the largest chunk maximum (lowest chunk on ties, because the
 //            row has the lowest index among its ties); the runner-up is either in the same chunk or is the
 //            best row outside it, which by the same argument is in the second-best chunk.
-//   phase 2: re-score those 64 rows with XOR+POPC and keep the exact top-2 by (distance, global index) --
-//            the reference tie-break.  Keys are (distance << 6 | position), position = 0..31 in the
-//            lower-index chunk, 32..63 in the higher one, so 32-bit min == (distance, global index) order.
+//   phase 2: re-score those 2 x chunk rows with XOR+POPC and keep the exact top-2 by (distance, global index).
+// Sharded path (ex.world > 0): the warp stores the query's keys straight into every peer's exchange buffer and the
+// kernel's last block publishes this rank's flags (exchange.cuh); exchange_wait_merge_kernel follows.
 template <int G>
 __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long base, unsigned long long *keys_out,
                                                         slm_exchange ex)
 {
     constexpr int kQPW = 32 / G;   // queries per warp
+    slm_pdl_launch_dependents();   // the exchange's wait + merge kernel may become resident while this one drains
     const int lane = threadIdx.x & 31, sub = lane % G;
     const long long gq = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kQPW + lane / G;
     const bool live = gq < (long long)p.n_prob * p.nq;
@@ -634,23 +645,16 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
         q = p.desc + (long long)pr.x * p.frame_words;
         t = p.desc + (long long)pr.y * p.frame_words;
     }
+    const uint4 *qs = reinterpret_cast<const uint4 *>(q + (long long)qi * 8);
+    const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);        // inputs of the call: readable before the search has finished
+    slm_pdl_wait();                                        // the candidate keys of the search kernel are visible from here
     // ---- phase 1 ----
     const int n_cand = p.cpg * p.n_epochs * 4;   // (unit, epoch, set, best/second)
     const float *cand = reinterpret_cast<const float *>(p.cand) + gqc * (long long)n_cand;
-    unsigned long long c1 = 0, c2 = 0;   // 0 = none; key = (dot + 257) << 32 | ~global_chunk
+    unsigned long long c1 = 0, c2 = 0;   // 0 = none
     auto consider = [&](int ci) {
         const float key = cand[ci];
-        if (key > -1.0e30f) {
-            // key = dot * 2^15 + (32767 - chunk counter of the unit's epoch); undo the unit's strided range walk
-            const int ki = (int)key + kKeyBias;
-            const int lc = kChunkMask - (ki & kChunkMask);
-            const int slot = ci >> 2, unit = slot / p.n_epochs, epoch = slot % p.n_epochs;
-            const int cpt = kTileN / p.chunk;                         // chunks per tile: 8 (or 16 in chained batches)
-            const int lt = lc / cpt;                                  // tile counter inside the epoch
-            const int range = unit + (epoch * p.rpe + lt / p.range_tiles) * p.cpg;
-            const unsigned gchunk = (unsigned)((range * p.range_tiles + lt % p.range_tiles) * cpt + (lc & (cpt - 1)));
-            top2_insert_max(c1, c2, ((unsigned long long)((ki >> kChunkBits) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk));
-        }
+        if (key > -1.0e30f) top2_insert_max(c1, c2, cand_to_chunk_key(p, key, ci >> 2));
     };
     if (n_cand <= 8) {
         for (int ci = 0; ci < n_cand; ++ci) consider(ci);          // every lane of the group scans all: no shuffles
@@ -668,23 +672,16 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
     unsigned ga = c1 ? 0xFFFFFFFFu - (unsigned)(c1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
     unsigned gb = c2 ? 0xFFFFFFFFu - (unsigned)(c2 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
     const unsigned glo = min(ga, gb), ghi = max(ga, gb);           // 0xFFFFFFFF = no such chunk
-    const uint4 *qs = reinterpret_cast<const uint4 *>(q + (long long)qi * 8);
-    const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
     unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const unsigned g = s == 0 ? glo : ghi;
         if (g == 0xFFFFFFFFu) continue;
-#pragma unroll
-        for (int j = 0; j < 32 / G; ++j) {
-            const int pos = j * G + sub;
+        for (int pos = sub; pos < p.chunk; pos += G) {
             const long long row = (long long)g * p.chunk + pos;
-            if (pos < p.chunk && row < p.nt) {
+            if (row < p.nt) {
                 const uint4 *ts = reinterpret_cast<const uint4 *>(t + row * 8);
-                const uint4 ta = __ldg(ts), tb = __ldg(ts + 1);
-                const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
-                                   __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
-                const unsigned key = (d << 6) | (unsigned)(s * 32 + pos);
+                const unsigned key = refine_key(hamming256(qa, qb, __ldg(ts), __ldg(ts + 1)), s, pos);
                 const unsigned m = max(k1, key);
                 k1 = min(k1, key);
                 k2 = min(k2, m);
@@ -700,69 +697,14 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
         k2 = min(min(k2, o2), m);
     }
     if (live && sub == 0) {
-        auto widen = [&](unsigned k) -> unsigned long long {
-            if (k == 0xFFFFFFFFu) return kKeyNone;
-            const unsigned pos = k & 63u;
-            const long long row = (long long)(pos < 32 ? glo : ghi) * p.chunk + (pos & 31u);
-            return ((unsigned long long)(k >> 6) << 32) | (unsigned long long)(base + row);
-        };
-        const ulonglong2 kk = make_ulonglong2(widen(k1), widen(k2));
-        if (keys_out) reinterpret_cast<ulonglong2 *>(keys_out)[gq] = kk;
-        if (ex.world > 0) {
-            // sharded path: this query's keys go straight into slot [step & 1][rank] of every peer's buffer
-            const long long slot = ((long long)(ex.step & 1u) * ex.world + ex.rank) * ex.cap + gq;
-            for (int r = 0; r < ex.world; ++r) reinterpret_cast<ulonglong2 *>(ex.peer_keys[r])[slot] = kk;
-        }
+        const unsigned long long w1 = refine_widen(k1, glo, ghi, p.chunk, base), w2 = refine_widen(k2, glo, ghi, p.chunk, base);
+        if (keys_out) reinterpret_cast<ulonglong2 *>(keys_out)[gq] = make_ulonglong2(w1, w2);
+        if (ex.world > 0) slm_exchange_store(ex, gq, w1, w2);
     }
-    if (ex.world > 0) {
-        // last-block-done: the block that finishes last publishes this rank's flags, waits (bounded) for every
-        // peer's keys of this step and merges + finalises all queries from the local buffer
-        __shared__ bool is_last;
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) is_last = atomicAdd(ex.done_counter, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (!is_last) return;
-        const unsigned parity = ex.step & 1u;
-        if (threadIdx.x == 0) *ex.done_counter = 0;
-        if ((int)threadIdx.x < ex.world) {
-            __threadfence_system();
-            unsigned *flag = ex.peer_flags[threadIdx.x] + parity * ex.world + ex.rank;
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(ex.step) : "memory");
-            const unsigned *mine = ex.peer_flags[ex.rank] + parity * ex.world + threadIdx.x;
-            unsigned v, spins = 0;
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-                if (++spins > (1u << 27)) {
-                    printf("slammatch: exchange flag of rank %d never reached step %u (have %u)\n", (int)threadIdx.x,
-                           ex.step, v);
-                    __trap();
-                }
-            } while ((int)(v - ex.step) < 0);
-        }
-        __syncthreads();
-        const unsigned long long *g = ex.peer_keys[ex.rank] + (long long)parity * ex.world * ex.cap * 2;
-        const long long n_q = (long long)p.n_prob * p.nq;
-        for (long long i = threadIdx.x; i < n_q; i += blockDim.x) {
-            unsigned long long m1 = kKeyNone, m2 = kKeyNone;
-            for (int r = 0; r < ex.world; ++r) {
-                const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(g)[(long long)r * ex.cap + i];
-                top2_insert(m1, m2, v.x);
-                top2_insert(m1, m2, v.y);
-            }
-            const bool has1 = m1 != kKeyNone, has2 = m2 != kKeyNone;
-            const int i1 = has1 ? (int)(m1 & 0xFFFFFFFFull) : -1, d1 = has1 ? (int)(m1 >> 32) : -1;
-            const int i2 = has2 ? (int)(m2 & 0xFFFFFFFFull) : -1, d2 = has2 ? (int)(m2 >> 32) : -1;
-            if (ex.idx_out) reinterpret_cast<int2 *>(ex.idx_out)[i] = make_int2(i1, i2);
-            if (ex.dist_out) reinterpret_cast<int2 *>(ex.dist_out)[i] = make_int2(d1, d2);
-            if (ex.accept_out)
-                ex.accept_out[i] = (ex.ratio_num > 0 ? (has1 && has2 && (long long)ex.ratio_den * d1 < (long long)ex.ratio_num * d2)
-                                                     : has1) ? 1 : 0;
-        }
-    }
+    if (ex.world > 0) slm_exchange_publish(ex);
 }
 
-// Refine for batches of frame-sized problems (config 3).  tc_refine_kernel reads every query's 64 candidate rows
+// Refine for batches of frame-sized problems (config 3).  tc_refine_kernel reads every query's candidate rows
 // straight from L2: 2 KB per query, 8 GB for 2016 pairs x 2000 queries -- L2-bandwidth bound (0.9 ms, as long as the
 // tensor kernel itself).  Here one CTA owns one pair, stages the pair's whole train frame in shared memory once
 // (64 KB for 2000 rows) and re-scores all of the pair's queries from there; what is left is the POPC pipe.
@@ -779,6 +721,7 @@ __global__ void __launch_bounds__(kRefineFrameThreads) tc_refine_frame_kernel(Tc
     // low halves of all rows first, then the high halves: the 8 lanes of a group read 8 consecutive rows, i.e.
     // 128 contiguous bytes per LDS.128 quarter-warp -- conflict-free (32-byte row stride would be 2-way)
     for (int i = threadIdx.x; i < 2 * p.nt; i += kRefineFrameThreads) s_rows[(i & 1) * p.nt + (i >> 1)] = __ldg(t4 + i);
+    slm_pdl_wait();
     __syncthreads();
     const int sub = threadIdx.x % G, grp = threadIdx.x / G;
     const float4 *cand4 = reinterpret_cast<const float4 *>(p.cand) + (long long)prob * p.nq;
@@ -801,7 +744,7 @@ __global__ void __launch_bounds__(kRefineFrameThreads) tc_refine_frame_kernel(Tc
         const unsigned ga = c1 ? 0xFFFFFFFFu - (unsigned)(c1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
         const unsigned gb = c2 ? 0xFFFFFFFFu - (unsigned)(c2 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
         const unsigned glo = min(ga, gb), ghi = max(ga, gb);
-        // ---- phase 2: exact re-scoring of those 64 rows from shared memory ----
+        // ---- phase 2: exact re-scoring of those rows from shared memory ----
         const uint4 *qs = reinterpret_cast<const uint4 *>(q + (long long)qc * 8);
         const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
         unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
@@ -809,15 +752,10 @@ __global__ void __launch_bounds__(kRefineFrameThreads) tc_refine_frame_kernel(Tc
         for (int s = 0; s < 2; ++s) {
             const unsigned g = s == 0 ? glo : ghi;
             if (g == 0xFFFFFFFFu) continue;
-#pragma unroll
-            for (int j = 0; j < 32 / G; ++j) {
-                const int pos = j * G + sub;
+            for (int pos = sub; pos < p.chunk; pos += G) {
                 const int row = (int)g * p.chunk + pos;
-                if (pos < p.chunk && row < p.nt) {
-                    const uint4 ta = s_rows[row], tb = s_rows[p.nt + row];
-                    const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
-                                       __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
-                    const unsigned key = (d << 6) | (unsigned)(s * 32 + pos);
+                if (row < p.nt) {
+                    const unsigned key = refine_key(hamming256(qa, qb, s_rows[row], s_rows[p.nt + row]), s, pos);
                     const unsigned m = max(k1, key);
                     k1 = min(k1, key);
                     k2 = min(k2, m);
@@ -831,29 +769,32 @@ __global__ void __launch_bounds__(kRefineFrameThreads) tc_refine_frame_kernel(Tc
             k1 = min(k1, o1);
             k2 = min(min(k2, o2), m);
         }
-        if (live && sub == 0) {
-            auto widen = [&](unsigned k) -> unsigned long long {
-                if (k == 0xFFFFFFFFu) return kKeyNone;
-                const unsigned pos = k & 63u;
-                const long long row = (long long)(pos < 32 ? glo : ghi) * p.chunk + (pos & 31u);
-                return ((unsigned long long)(k >> 6) << 32) | (unsigned long long)row;
-            };
-            reinterpret_cast<ulonglong2 *>(keys_out)[(long long)prob * p.nq + qi] = make_ulonglong2(widen(k1), widen(k2));
-        }
+        if (live && sub == 0)
+            reinterpret_cast<ulonglong2 *>(keys_out)[(long long)prob * p.nq + qi] =
+                make_ulonglong2(refine_widen(k1, glo, ghi, p.chunk, 0), refine_widen(k2, glo, ghi, p.chunk, 0));
     }
+}
+
+// cudaFuncSetAttribute once per (kernel, device); the flag is atomic so concurrent first calls from two host
+// threads are benign (setting the attribute twice is harmless)
+template <typename K>
+int configure_smem(K kernel, std::atomic<bool> (&configured)[64], size_t smem)
+{
+    int dev = 0;
+    SLM_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63].load(std::memory_order_acquire)) {
+        SLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev & 63].store(true, std::memory_order_release);
+    }
+    return SLM_OK;
 }
 
 template <int MT>
 int launch_tc(const TcParams &p, int n_prob, cudaStream_t stream)
 {
     const size_t smem = (size_t)MT * kATileBytes + 2 * kBTileBytes + sizeof(TcBarriers) + 64;
-    static bool configured[64] = {};
-    int dev = 0;
-    SLM_CUDA(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        SLM_CUDA(cudaFuncSetAttribute(knn2_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev & 63] = true;
-    }
+    static std::atomic<bool> configured[64];
+    SLM_TRY(configure_smem(knn2_tc_kernel<MT>, configured, smem));
     dim3 grid((unsigned)(p.n_groups * p.n_ranges), (unsigned)n_prob);
     knn2_tc_kernel<MT><<<grid, kThreads, smem, stream>>>(p);
     SLM_CUDA(cudaGetLastError());
@@ -864,13 +805,8 @@ template <int MT, bool CHAIN>
 int launch_tc2_impl(const TcParams &p, int n_prob, cudaStream_t stream)
 {
     const size_t smem = (size_t)MT * kATileBytes + kBStages2 * kBHalfBytes + sizeof(TcBarriers2) + 64;
-    static bool configured[64] = {};
-    int dev = 0;
-    SLM_CUDA(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        SLM_CUDA(cudaFuncSetAttribute(knn2_tc2_kernel<MT, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev & 63] = true;
-    }
+    static std::atomic<bool> configured[64];
+    SLM_TRY(configure_smem(knn2_tc2_kernel<MT, CHAIN>, configured, smem));
     const int n_gpairs = (p.n_groups + 1) / 2;
     dim3 grid((unsigned)(2 * n_gpairs * p.cpg), (unsigned)n_prob);
     knn2_tc2_kernel<MT, CHAIN><<<grid, kThreads2, smem, stream>>>(p);
@@ -884,17 +820,48 @@ int launch_tc2(const TcParams &p, int n_prob, cudaStream_t stream)
     return p.chain_pairs ? launch_tc2_impl<MT, true>(p, n_prob, stream) : launch_tc2_impl<MT, false>(p, n_prob, stream);
 }
 
-int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_out, cudaStream_t stream,
-           const slm_exchange *exchange = nullptr, const slm_chain *chain = nullptr)
+// Clusters per unit for the resident-cluster kernels: minimise  waves x (start-up + tiles per cluster x cycles per tile)
+// with waves = ceil(units * cpg / cluster slots).  Few units (long train sets) end up as one resident wave, many units
+// as several waves of longer-lived clusters.
+long long plan_cpg(const slm_ctx *ctx, long long units, long long n_tiles, double startup_clk, double tile_clk)
 {
-    ctx->last_variant = SLM_VARIANT_TENSOR;
+    const long long slots = ctx->sm_count / 2;
+    long long cpg = 1;
+    double best = 1e300;
+    long long cpg_max = n_tiles < 4 * slots ? n_tiles : 4 * slots;
+    if (cpg_max > ctx->max_cpg) cpg_max = ctx->max_cpg;
+    for (long long c = 1; c <= cpg_max; ++c) {
+        const long long waves = (units * c + slots - 1) / slots;
+        const double cost = (double)waves * (startup_clk + (double)((n_tiles + c - 1) / c) * tile_clk);
+        if (cost < best * 0.999) { best = cost; cpg = c; }
+    }
+    return cpg;
+}
+
+int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_out, cudaStream_t stream,
+           const slm_exchange *exchange = nullptr, const slm_chain *chain = nullptr, bool allow_fp4 = true)
+{
     p.n_prob = n_prob;
     const int m_tiles = (p.nq + kTileM - 1) / kTileM;
-    const int n_tiles = (p.nt + kTileN - 1) / kTileN;
     // CTA pairs (cta_group::2) need at least two query tiles to keep both halves of the M = 256 MMA busy
     const bool two_cta = m_tiles >= 2 && !ctx->force_1cta;
-    int work_units;                      // CTAs (1-CTA kernel) or CTA pairs (2-CTA kernel) per train range
-    if (two_cta) {
+    // fp4 (kind::mxf4, twice the fp8 rate) whenever CTA pairs apply; batches of frame-sized problems stay on the
+    // fp8 kernel (their chained instantiation and shared-memory refine are tuned for 16-row chunks)
+    const bool fp4 = two_cta && allow_fp4 && p.desc == nullptr;
+    ctx->last_variant = fp4 ? SLM_VARIANT_TENSOR4 : SLM_VARIANT_TENSOR;
+    p.tile_n = fp4 ? tc4::kTileN : kTileN;
+    const int n_tiles = (p.nt + p.tile_n - 1) / p.tile_n;
+    const long long n_q = (long long)n_prob * p.nq;
+    int work_units;                      // CTAs (1-CTA kernel) or CTA pairs (2-CTA kernels) per train range
+    if (fp4) {
+        int n_groups = 2 * ((m_tiles + 2 * kMaxMT4 - 1) / (2 * kMaxMT4));
+        p.mt = (m_tiles + n_groups - 1) / n_groups;
+        p.n_groups = (m_tiles + p.mt - 1) / p.mt;
+        work_units = (p.n_groups + 1) / 2;
+        // wide chunks keep the hot kernel's epilogue at 0.52 ALU ops per element; the refine pass re-scores two chunks per
+        // query, so many-query problems take narrower ones
+        p.chunk = ctx->tc4_chunk > 0 ? ctx->tc4_chunk : (n_q <= 32768 ? 120 : 40);
+    } else if (two_cta) {
         // split the query tiles evenly over an even number of groups of at most kMaxMT2 tiles
         int n_groups = 2 * ((m_tiles + 2 * kMaxMT2 - 1) / (2 * kMaxMT2));
         p.mt = (m_tiles + n_groups - 1) / n_groups;
@@ -902,7 +869,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
             // EXPERIMENTAL (SLM_TC_PLAN_MT=1, off by default): also choose the query tiles per CTA.
             // Fewer tiles per CTA = more, shorter-lived clusters with less to expand at start-up -- better for
             // mid-size problems (c2: 2000 x 20000) where the start-up dominates.  Start-up model: 6000 + 2000 per
-            // query tile (14000 at 4 tiles, the measured figure); to be calibrated before it becomes the default.
+            // query tile (14000 at 4 tiles, the measured figure).
             const long long slots = ctx->sm_count / 2;
             double best = 1e300;
             int best_mt = p.mt;
@@ -920,35 +887,30 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         }
         p.n_groups = (m_tiles + p.mt - 1) / p.mt;
         work_units = (p.n_groups + 1) / 2;
+        p.chunk = kChunk;
     } else {
         p.mt = m_tiles >= kMaxMT ? kMaxMT : m_tiles;
         p.n_groups = (m_tiles + p.mt - 1) / p.mt;
         work_units = p.n_groups;
+        p.chunk = kChunk;
     }
     if (two_cta) {
         // CTA pairs.  `units` = (group pair, problem) combinations; each gets `cpg` clusters that walk the train
         // ranges with stride cpg.  Few units (long train sets): one resident wave, the query tiles are expanded
-        // once per cluster and short ranges keep the static stride balanced.  Many units: ~16 waves of clusters.
-        const long long slots = ctx->sm_count / 2;
+        // once per cluster and short ranges keep the static stride balanced.  Many units: several waves of clusters.
         const long long units = (long long)work_units * n_prob;
-        // Clusters per unit: minimise  waves x (start-up + tiles per cluster x cycles per tile)  with
-        // waves = ceil(units * cpg / cluster slots).  Few units (long train sets) end up as one resident wave,
-        // many units as several waves of longer-lived clusters.
-        const double kStartupClk = ctx->tc_plan_mt ? 6000.0 + 2000.0 * p.mt : 14000.0, kTileClk = 1024.0 * p.mt;
-        long long cpg = 1;
-        double best = 1e300;
-        long long cpg_max = n_tiles < 4 * slots ? n_tiles : 4 * slots;
-        if (cpg_max > ctx->max_cpg) cpg_max = ctx->max_cpg;
-        for (long long c = 1; c <= cpg_max; ++c) {
-            const long long waves = (units * c + slots - 1) / slots;
-            const double cost = (double)waves * (kStartupClk + (double)((n_tiles + c - 1) / c) * kTileClk);
-            if (cost < best * 0.999) { best = cost; cpg = c; }
-        }
+        const double startup = fp4 ? 8000.0 + 1500.0 * p.mt : (ctx->tc_plan_mt ? 6000.0 + 2000.0 * p.mt : 14000.0);
+        const double tile_clk = (fp4 ? 2.0 * tc4::kTileN : 1024.0) * p.mt;
+        const long long cpg = plan_cpg(ctx, units, n_tiles, startup, tile_clk);
         long long range_tiles = n_tiles / (cpg * 128);      // short ranges: the static stride stays balanced
         if (range_tiles < 1) range_tiles = 1;
         if (range_tiles > 8) range_tiles = 8;
         const long long n_ranges = (n_tiles + range_tiles - 1) / range_tiles;
-        const long long rpe = ctx->epoch_tiles / range_tiles;      // <= kMaxEpochTiles tiles per epoch
+        // chunk counters of one candidate epoch must fit the key's 15 bits
+        long long epoch_tiles = (1 << kChunkBits) / (p.tile_n / p.chunk);
+        if (epoch_tiles > ctx->epoch_tiles) epoch_tiles = ctx->epoch_tiles;
+        long long rpe = epoch_tiles / range_tiles;
+        if (rpe < 1) rpe = 1;
         const long long ranges_per_unit = (n_ranges + cpg - 1) / cpg;
         p.cpg = (int)cpg;
         p.range_tiles = (int)range_tiles;
@@ -979,8 +941,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     // Chained batch: short train frames (one cluster per query-group pair walks a whole frame in one epoch) whose
     // pairs share query frames -- grid.y runs over the units instead of the pairs.
     int grid_y = n_prob;
-    p.chunk = kChunk;
-    if (chain && two_cta && p.cpg == 1 && p.n_epochs == 1 && chain->n_units > 0 && chain->n_units < n_prob &&
+    if (!fp4 && chain && two_cta && p.cpg == 1 && p.n_epochs == 1 && chain->n_units > 0 && chain->n_units < n_prob &&
         n_tiles <= kMaxEpochTiles / 2) {
         p.chunk = 16;      // the chained instantiation tracks 16-column candidate chunks
         p.chain_pairs = chain->pairs_sorted;
@@ -992,9 +953,11 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     SLM_TRY(slm_buf_reserve(ctx, &ctx->scratch, cand_bytes));
     p.cand = reinterpret_cast<float2 *>(ctx->scratch.p);
 
-    ctx->last_kernel = two_cta ? "knn2_tc2_kernel" : "knn2_tc_kernel";
+    ctx->last_kernel = fp4 ? "knn2_tc4_kernel" : two_cta ? "knn2_tc2_kernel" : "knn2_tc_kernel";
     SLM_TRY(slm_prof_begin(ctx, stream));
-    if (two_cta) {
+    if (fp4) {
+        SLM_TRY(slm_tc4_launch(ctx, p, grid_y, stream));
+    } else if (two_cta) {
         switch (p.mt) {
         case 1: SLM_TRY(launch_tc2<1>(p, grid_y, stream)); break;
         case 2: SLM_TRY(launch_tc2<2>(p, grid_y, stream)); break;
@@ -1009,30 +972,26 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         }
     }
     SLM_TRY(slm_prof_end(ctx, stream));
-    const long long n_q = (long long)n_prob * p.nq;
     slm_exchange ex{};
     if (exchange) ex = *exchange;
     const size_t frame_smem = (size_t)p.nt * 32;
+    // the refine kernels start under programmatic dependent launch: their prologue (query loads, train-frame staging)
+    // overlaps the drain of the search kernel, which releases its dependents at start-up
+    const bool pdl = !ctx->no_pdl;
     if (p.desc != nullptr && !exchange && p.cpg * p.n_epochs == 1 && n_prob >= ctx->sm_count && frame_smem <= 200 * 1024 &&
         !ctx->no_frame_refine) {
         // batch of frame-sized problems: one CTA per pair, train frame staged in shared memory
-        static bool configured[64] = {};
-        int dev = 0;
-        SLM_CUDA(cudaGetDevice(&dev));
-        if (!configured[dev & 63]) {
-            SLM_CUDA(cudaFuncSetAttribute(tc_refine_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured[dev & 63] = true;
-        }
-        tc_refine_frame_kernel<<<(unsigned)n_prob, kRefineFrameThreads, frame_smem, stream>>>(
-            p, reinterpret_cast<unsigned long long *>(keys_out));
+        static std::atomic<bool> configured[64];
+        SLM_TRY(configure_smem(tc_refine_frame_kernel, configured, 200 * 1024));
+        SLM_CUDA(slm_launch(tc_refine_frame_kernel, dim3((unsigned)n_prob), dim3(kRefineFrameThreads), frame_smem, stream, pdl, p,
+                            reinterpret_cast<unsigned long long *>(keys_out)));
     } else if (p.cpg * p.n_epochs * 4 <= 32) {   // few candidates per query (many queries, short train sets): 8 lanes each
-        tc_refine_kernel<8><<<(unsigned)((n_q + 31) / 32), 256, 0, stream>>>(
-            p, base, reinterpret_cast<unsigned long long *>(keys_out), ex);
+        SLM_CUDA(slm_launch(tc_refine_kernel<8>, dim3((unsigned)((n_q + 31) / 32)), dim3(256), 0, stream, pdl, p, base,
+                            reinterpret_cast<unsigned long long *>(keys_out), ex));
     } else {                          // many ranges (long train sets): a full warp per query
-        tc_refine_kernel<32><<<(unsigned)((n_q + 7) / 8), 256, 0, stream>>>(
-            p, base, reinterpret_cast<unsigned long long *>(keys_out), ex);
+        SLM_CUDA(slm_launch(tc_refine_kernel<32>, dim3((unsigned)((n_q + 7) / 8)), dim3(256), 0, stream, pdl, p, base,
+                            reinterpret_cast<unsigned long long *>(keys_out), ex));
     }
-    SLM_CUDA(cudaGetLastError());
     ctx->launches += 2;
     return SLM_OK;
 }
@@ -1040,21 +999,21 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
 }  // namespace
 
 int slm_tc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
-                     uint64_t *keys_out, cudaStream_t stream)
+                     uint64_t *keys_out, cudaStream_t stream, bool fp4)
 {
     TcParams p{};
     p.q = q; p.t = t; p.desc = nullptr; p.pairs = nullptr; p.frame_words = 0;
     p.nq = (int)nq; p.nt = (int)nt;
-    return tc_run(ctx, p, 1, base, keys_out, stream);
+    return tc_run(ctx, p, 1, base, keys_out, stream, nullptr, nullptr, fp4);
 }
 
 int slm_tc_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
-                         const slm_exchange &ex, cudaStream_t stream)
+                         const slm_exchange &ex, cudaStream_t stream, bool fp4)
 {
     TcParams p{};
     p.q = q; p.t = t; p.desc = nullptr; p.pairs = nullptr; p.frame_words = 0;
     p.nq = (int)nq; p.nt = (int)nt;
-    return tc_run(ctx, p, 1, base, nullptr, stream, &ex);
+    return tc_run(ctx, p, 1, base, nullptr, stream, &ex, nullptr, fp4);
 }
 
 int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
@@ -1064,5 +1023,5 @@ int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_f
     p.q = nullptr; p.t = nullptr; p.desc = desc; p.pairs = pairs_dev;
     p.frame_words = n_per_frame * 8;
     p.nq = (int)n_per_frame; p.nt = (int)n_per_frame;
-    return tc_run(ctx, p, (int)n_pairs, 0, keys_out, stream, nullptr, chain);
+    return tc_run(ctx, p, (int)n_pairs, 0, keys_out, stream, nullptr, chain, false);
 }

@@ -48,12 +48,26 @@ struct slm_ctx {
     cudaEvent_t chunk_ev[kMaxHostChunks] = {};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // optional timing of the dominant kernel (slm_profile_enable)
-    unsigned *done_counter = nullptr;   // 4-byte device counter (slm_tc_knn2_exchange)
+    unsigned *done_counter = nullptr;   // 4-byte device counter (last-block-done of the exchange producers)
+    // sharded exchange (exchange.cu)
+    int *exchange_status = nullptr;     // mapped pinned int[4]: (code, rank, step, value seen) written by the merge kernel
+    long long exchange_max_blocks = 296;   // grid cap of the wait + merge kernel (SLM_EXCHANGE_MAX_BLOCKS; loopback tests lower it)
+    unsigned exchange_max_polls = 1u << 23;   // flag polls before a peer is reported lost (~4 s; SLM_EXCHANGE_MAX_POLLS)
+    int exchange_wide_keys = 0;         // SLM_EXCHANGE_WIDE_KEYS: always exchange 64-bit keys (A/B of the compact form)
+    // stream bookkeeping: every device entry point runs between slm_enter() and slm_leave()
+    cudaStream_t cur_stream = nullptr;  // stream of the call in progress (workspace growth is ordered on it)
+    cudaStream_t last_stream = nullptr; // stream of the previous call
+    cudaEvent_t last_ev = nullptr;      // recorded at the end of every call on its stream
+    bool have_last = false;
+    int tc_fp4 = 1;                     // AUTO uses the mxf4 tensor kernel where it applies (SLM_TC_FP4=0: fp8 only)
+    int tc4_chunk = 0;                  // SLM_TC4_CHUNK: force the fp4 kernel's candidate chunk width (120 or 40; tests / A-B)
+    int no_pdl = 0;                     // SLM_NO_PDL: launch the refine / merge kernels without programmatic dependent launch
     int profile = 0;
     static constexpr int kMaxProf = 4096;
     cudaEvent_t *prof_ev = nullptr;   // kMaxProf events, created lazily
     unsigned char *prof_tag = nullptr;
     int prof_n = 0;
+    long long prof_dropped = 0;       // marks lost because the buffer was full (reported by slm_profile_read)
     int trace = 0;                    // SLM_TRACE=1: slm_profile_read prints every interval to stderr
 };
 
@@ -79,9 +93,34 @@ int slm_fail(int code, const char *fmt, ...);
         if (r__ != SLM_OK) return r__; \
     } while (0)
 
-// Grow `buf` to at least `bytes` (device-synchronises before freeing the old block, so kernels of
-// earlier calls that still use it have finished).
+// Grow `buf` to at least `bytes`.  Inside a call (slm_enter .. slm_leave) the old block is released and the new one
+// allocated in stream order on the call's stream (cudaFreeAsync / cudaMallocAsync): kernels of earlier calls that
+// still use the old block finish first, and nothing synchronises the device.
 int slm_buf_reserve(slm_ctx *ctx, slm_buf *buf, size_t bytes);
+
+// Stream bookkeeping of the device entry points.  The workspace of a ctx (keys / scratch / tickets ...) is shared by
+// all calls, so a call on another stream than the previous one first waits (on the device) for that call's work.
+int slm_enter(slm_ctx *ctx, cudaStream_t stream);
+int slm_leave(slm_ctx *ctx, cudaStream_t stream);
+
+// Kernel launch through cudaLaunchKernelEx; pdl = programmatic dependent launch (the kernel may start while the
+// previous kernel of the stream drains; it must order itself with griddepcontrol.wait or its own flags).
+template <typename... KArgs, typename... Args>
+inline cudaError_t slm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                              Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- variant P: LOP3(XOR)+POPC on the integer pipe (knn2_popc.cu) --------------------------------
 // Single problem or a batch of equally-shaped problems (n_prob >= 1, pairs given by frame indices).
@@ -123,36 +162,41 @@ int slm_merge_finalize(slm_ctx *ctx, const uint64_t *gathered, int32_t n_shards,
                        int32_t ratio_den, int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
 int slm_gather(slm_ctx *ctx, const void *src, int32_t row_bytes, const int32_t *matches, const int32_t *count,
                int64_t capacity, int32_t column, void *out, cudaStream_t stream);
-int slm_exchange_merge_impl(slm_ctx *ctx, const uint64_t *local_keys, int64_t nq, int64_t cap,
-                            const uint64_t *peer_keys_host, const uint64_t *peer_flags_host, int32_t rank, int32_t world,
-                            uint32_t step, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out, int32_t *dist_out,
-                            uint8_t *accept_out, cudaStream_t stream);
+int slm_filter_points3d_impl(slm_ctx *ctx, const double *pts3d, int64_t n, double max_distance, uint8_t *accept,
+                             cudaStream_t stream);
 int slm_compact(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uint8_t *accept, int64_t nq,
                 int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, cudaStream_t stream);
 
-// ---- NVLink exchange of per-rank keys (sharded path) ---------------------------------------------------
-// Every rank's key buffer uint64[2][world][cap][2] and flag array uint32[2][world] are peer-mapped on this GPU.
+// ---- NVLink exchange of per-rank keys (sharded path; protocol in exchange.cuh) --------------------------------
+// Every rank's key buffer [2][world][cap][2] keys and flag array uint32[2][world] are peer-mapped on this GPU.
 static constexpr int kSlmMaxWorld = 16;
 struct slm_exchange {
-    unsigned long long *peer_keys[kSlmMaxWorld];
+    unsigned char *peer_keys[kSlmMaxWorld];
     unsigned *peer_flags[kSlmMaxWorld];
     int rank, world;
     unsigned step;
     long long cap;
-    // outputs of the fused merge + finalize
-    int ratio_num, ratio_den;
-    int *idx_out, *dist_out;
-    unsigned char *accept_out;
+    int key_bytes;            // 8: uint64 keys (distance << 32 | index); 4: compact uint32 keys (distance << 16 | index)
     unsigned *done_counter;   // device counter for the last-block-done pattern (zero between launches)
 };
+int slm_exchange_setup(slm_ctx *ctx, slm_exchange *ex, const uint64_t *peer_keys_host, const uint64_t *peer_flags_host,
+                       int32_t rank, int32_t world, uint32_t step, int64_t cap, int64_t nt_global);
+// producer for keys that already sit in local memory (non-tensor variants)
+int slm_exchange_store(slm_ctx *ctx, const slm_exchange &ex, const uint64_t *local_keys, int64_t nq, cudaStream_t stream);
+// wait for every rank's keys of this step, merge, finalise
+int slm_exchange_wait_merge(slm_ctx *ctx, const slm_exchange &ex, int64_t nq, int32_t ratio_num, int32_t ratio_den,
+                            int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
+// SLM_ERR_TIMEOUT if an earlier merge kernel reported a lost peer (clears the report)
+int slm_exchange_check(slm_ctx *ctx);
 
 // ---- variant T: +-1 fp8 expansion + tcgen05.mma with TMEM accumulators (knn2_tc.cu) ---------------
+// fp4 = true: kind::mxf4 kernel (knn2_tc4.cu) where CTA pairs apply, else the fp8 kernels
 int slm_tc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
-                     int64_t base, uint64_t *keys_out, cudaStream_t stream);
-// Search + NVLink exchange + merge + finalize: the refine kernel stores each query's keys straight into every
-// peer's buffer; its last block publishes the flags, waits for the peers and merges (no separate kernel).
+                     int64_t base, uint64_t *keys_out, cudaStream_t stream, bool fp4);
+// Search + NVLink exchange: the refine kernel stores each query's keys straight into every peer's buffer and its
+// last block publishes the flags (the caller follows with slm_exchange_wait_merge).
 int slm_tc_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
-                         const slm_exchange &ex, cudaStream_t stream);
+                         const slm_exchange &ex, cudaStream_t stream, bool fp4);
 // Chained batch (config 3): the caller's pairs sorted by query frame and cut into units of pairs that share it
 // (all device arrays; see TcParams in knn2_tc.cu).  Optional: nullptr = every pair is its own launch item.
 struct slm_chain {

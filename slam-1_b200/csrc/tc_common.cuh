@@ -320,3 +320,90 @@ __device__ __forceinline__ void umma_job(uint32_t tmem_d, uint32_t a_lo, uint32_
 }
 
 }  // namespace tc
+
+// =====================================================================================================
+// Variant T4: the same contraction on the block-scaled FP4 path (tcgen05.mma kind::mxf4, twice the fp8 rate).
+// +-1 is exact in e2m1 (+1.0 = 0x2, -1.0 = 0xA), every UE8M0 block scale is 1.0 (0x7F), so
+// dot(x, y) = 256 - 2 * Hamming(a, b) still holds exactly in the fp32 accumulator.
+// Operand layout: K-major, no swizzle, 4-bit elements: core matrix = 8 rows x 16 bytes (32 values),
+//   LBO = 128 B between the 8 K-chunks of a row group, SBO = 1024 B between 8-row groups; byte (row r, chunk c) at
+//   (r / 8) * 1024 + c * 128 + (r % 8) * 16.  One MMA consumes K = 64 = 2 chunks (descriptor start + 256 B).
+// TMEM: two 240-column accumulators + 32 scale-factor columns (all bytes 0x7F, so the scale-factor layout is moot)
+// fill the 512 columns; a job is therefore 256 query rows (CTA pair) x 240 train rows.
+// Validated stand-alone by csrc/microbench/fp4_probe2.cu (profiles/r2_fp4_probe.txt): exact, 16381 MAC/clk/SM.
+// =====================================================================================================
+namespace tc4 {
+
+constexpr int kTileN = 240;                        // train rows per job (N of the MMA; 120 per CTA of the pair)
+constexpr int kHalfN = kTileN / 2;
+constexpr uint32_t kSfCol = 2 * kTileN;            // TMEM columns [480, 512)
+constexpr uint32_t kScaleOnes = 0x7F7F7F7Fu;       // four UE8M0 1.0
+constexpr uint32_t kE2m1PlusOne = 0x22222222u;     // eight e2m1 +1.0; bit 3 of a nibble set => -1.0
+constexpr uint32_t kLBO = 128, kSBO = 1024;
+constexpr uint32_t kRowBytes = 128;                // 256 e2m1 values
+constexpr uint32_t kATileBytes = 128 * kRowBytes;  // 16 KB: 128 query rows
+constexpr uint32_t kBHalfBytes = kHalfN * kRowBytes;   // 15 KB: this CTA's 120 rows of a train tile
+constexpr uint32_t kDescHi = (kSBO >> 4) | (1u << 14);
+
+// Instruction descriptor of the block-scaled kinds (cute/arch/mma_sm100_desc.hpp, InstrDescriptorBlockScaled):
+// a_format [7,10) = b_format [10,13) = 1 (MXF4 E2M1), both K-major, N >> 3 in [17,23), scale format [23] = 1 (UE8M0),
+// M >> 4 in [24,29), scale-factor ids 0, K = 64.
+__host__ __device__ constexpr uint32_t idesc_mxf4(uint32_t M, uint32_t N)
+{
+    return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | ((kLBO >> 4) << 16); }
+
+// cta_group::2, leader CTA, one thread; `sf` = TMEM address of the scale-factor columns (same for A and B)
+__device__ __forceinline__ void umma_mxf4_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                             uint32_t sf)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "mov.b64 da, {%1, %4};\n\t"
+                 "mov.b64 db, {%2, %4};\n\t"
+                 "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], da, db, %3, [%6], [%6], p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kDescHi), "r"(accumulate), "r"(sf) : "memory");
+}
+// One job = 4 MMAs over K = 256.
+__device__ __forceinline__ void umma_job(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t sf)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_mxf4_lo(tmem_d, a_lo + k * 16, b_lo + k * 16, idesc, k > 0 ? 1u : 0u, sf);
+}
+
+// 32 lanes x 32 columns <- one 32-bit value (whole warp, its own lane quarter)
+__device__ __forceinline__ void tmem_fill32(uint32_t taddr, uint32_t v)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n\t"
+        "tcgen05.wait::st.sync.aligned;"
+        ::"r"(taddr), "r"(v) : "memory");
+}
+
+// One 32-bit descriptor word -> one 16-byte K-chunk: output word j takes bits {3-j, 7-j, ..., 31-j} of w onto the sign
+// bits of its eight nibbles (the K permutation is shared by both operands): 1 shift + 1 LOP3 per 8 values.
+__device__ __forceinline__ void expand_word_to_smem(uint32_t addr, uint32_t w)
+{
+    const uint32_t o0 = (w & 0x88888888u) | kE2m1PlusOne;
+    const uint32_t o1 = ((w << 1) & 0x88888888u) | kE2m1PlusOne;
+    const uint32_t o2 = ((w << 2) & 0x88888888u) | kE2m1PlusOne;
+    const uint32_t o3 = ((w << 3) & 0x88888888u) | kE2m1PlusOne;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+}
+// byte offset of (row, K-chunk) inside an operand tile
+__device__ __forceinline__ uint32_t tile_offset(int row, int chunk)
+{
+    return (uint32_t)(row >> 3) * kSBO + (uint32_t)chunk * kLBO + (uint32_t)(row & 7) * 16;
+}
+__device__ __forceinline__ void expand_row_to_smem(uint32_t tile, int row, const uint4 &d0, const uint4 &d1)
+{
+    const uint32_t base = tile + tile_offset(row, 0);
+    const uint32_t w[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) expand_word_to_smem(base + i * kLBO, w[i]);
+}
+
+}  // namespace tc4

@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(PKG_DIR, "libslammatch.so")
 
 SLM_OK = 0
-VARIANTS = {"auto": 0, "popc": 1, "tensor": 2, "bmma": 3}
+VARIANTS = {"auto": 0, "popc": 1, "tensor": 2, "bmma": 3, "tensor4": 4}
 
 # every symbol include/slammatch.h declares (tests check the library exports all of them)
 SYMBOLS = (
@@ -21,9 +21,9 @@ SYMBOLS = (
     "slm_launch_count", "slm_last_kernel",
     "slm_profile_enable", "slm_profile_read",
     "slm_knn2", "slm_knn2_keys", "slm_knn2_filter", "slm_knn2_batched", "slm_merge_top2",
-    "slm_exchange_merge", "slm_knn2_exchange",
-    "slm_compact_matches", "slm_gather_rows", "slm_bow_hist", "slm_chi2_scan", "slm_vocab_update",
-    "slm_knn2_host",
+    "slm_exchange_merge", "slm_knn2_exchange", "slm_exchange_status",
+    "slm_compact_matches", "slm_gather_rows", "slm_filter_points3d", "slm_bow_hist", "slm_chi2_scan", "slm_vocab_update",
+    "slm_knn2_host", "slm_probe_tensor_peak", "slm_probe_popc_peak",
 )
 
 _lib = None
@@ -70,9 +70,13 @@ def load():
         lib.slm_knn2_filter.argtypes = [vp, vp, i64, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp]
         lib.slm_knn2_batched.argtypes = [vp, vp, i64, i64, vp, i64, i32, i32, vp, vp, vp, vp]
         lib.slm_merge_top2.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, vp]
-        lib.slm_exchange_merge.argtypes = [vp, vp, i64, i64, vp, vp, i32, i32, ctypes.c_uint32, i32, i32, vp, vp, vp, vp]
-        lib.slm_knn2_exchange.argtypes = [vp, vp, i64, vp, i64, i64, i64, vp, vp, i32, i32, ctypes.c_uint32, i32, i32,
+        lib.slm_exchange_merge.argtypes = [vp, vp, i64, i64, i64, vp, vp, i32, i32, ctypes.c_uint32, i32, i32, vp, vp, vp, vp]
+        lib.slm_knn2_exchange.argtypes = [vp, vp, i64, vp, i64, i64, i64, i64, vp, vp, i32, i32, ctypes.c_uint32, i32, i32,
                                           vp, vp, vp, vp]
+        lib.slm_exchange_status.argtypes = [vp]
+        lib.slm_filter_points3d.argtypes = [vp, vp, i64, ctypes.c_double, vp, vp]
+        lib.slm_probe_tensor_peak.argtypes = [vp, i32, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        lib.slm_probe_popc_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         lib.slm_compact_matches.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
         lib.slm_gather_rows.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp, vp]
         lib.slm_bow_hist.argtypes = [vp, vp, i64, i32, i32, vp, vp]
@@ -101,10 +105,30 @@ class Context:
         check(self.lib.slm_create(int(device), ctypes.byref(h)))
         self.handle = h
         self.device = int(device)
+        self.variant = 0
 
     def set_variant(self, variant):
         v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
         check(self.lib.slm_set_variant(self.handle, v))
+        self.variant = v
+
+    def using(self, variant):
+        """Context manager: run with ``variant`` (None = leave as is) and restore the previous setting afterwards, so a
+        per-call ``variant=`` argument never leaks into later calls on the cached per-thread ctx."""
+        return _VariantScope(self, variant)
+
+    def probe_tensor_peak(self, kind: str = "f8f6f4", loops: int = 2048, reps: int = 5):
+        """(dense TFLOP/s, MAC/clk/SM) of back-to-back tcgen05.mma on every SM, measured now, in this process."""
+        tf, mac = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        check(self.lib.slm_probe_tensor_peak(self.handle, {"f8f6f4": 0, "mxf4": 1}[kind], int(loops), int(reps),
+                                             ctypes.byref(tf), ctypes.byref(mac)))
+        return tf.value, mac.value
+
+    def probe_popc_peak(self, reps: int = 5):
+        """(Tcmp/s, POPC32 lanes/clk/SM) of the integer-pipe comparison loop on every SM, measured now."""
+        tc, lanes = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        check(self.lib.slm_probe_popc_peak(self.handle, int(reps), ctypes.byref(tc), ctypes.byref(lanes)))
+        return tc.value, lanes.value
 
     def last_variant(self) -> str:
         v = int(self.lib.slm_last_variant(self.handle))
@@ -136,6 +160,22 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class _VariantScope:
+    def __init__(self, ctx, variant):
+        self.ctx, self.variant, self.prev = ctx, variant, None
+
+    def __enter__(self):
+        if self.variant is not None:
+            self.prev = self.ctx.variant
+            self.ctx.set_variant(self.variant)
+        return self.ctx
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            self.ctx.set_variant(self.prev)
+        return False
 
 
 _ctx_cache: dict = {}

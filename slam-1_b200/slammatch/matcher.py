@@ -114,16 +114,15 @@ def knn2(q, t, ratio=REFERENCE_RATIO, cross_check: bool = False, device: int | N
     q = _as_desc(q, "queryDescriptors")
     t = _as_desc(t, "trainDescriptors")
     ctx = _lib.context(0 if device is None else device)
-    if variant is not None:
-        ctx.set_variant(variant)
     nq, nt = q.shape[0], t.shape[0]
     idx = np.full((nq, 2), -1, dtype=np.int32)
     dist = np.full((nq, 2), -1, dtype=np.int32)
     acc = np.zeros(nq, dtype=np.uint8)
     if nq:
-        _lib.check(ctx.lib.slm_knn2_host(ctx.handle, q.ctypes.data, nq, t.ctypes.data if nt else None, nt,
-                                         num, den, int(bool(cross_check)), idx.ctypes.data, dist.ctypes.data,
-                                         acc.ctypes.data))
+        with ctx.using(variant):
+            _lib.check(ctx.lib.slm_knn2_host(ctx.handle, q.ctypes.data, nq, t.ctypes.data if nt else None, nt,
+                                             num, den, int(bool(cross_check)), idx.ctypes.data, dist.ctypes.data,
+                                             acc.ctypes.data))
         if train_index_base:
             idx[idx >= 0] += train_index_base
     return idx, dist, acc
@@ -148,17 +147,16 @@ def _knn2_device(q, t, num, den, cross_check, base, variant):
     t = _dev_desc(t, "trainDescriptors")
     dev = q.device
     ctx = _lib.context(dev.index or 0)
-    if variant is not None:
-        ctx.set_variant(variant)
     nq, nt = q.shape[0], t.shape[0]
     idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
     dist = torch.empty((nq, 2), dtype=torch.int32, device=dev)
     acc = torch.empty((nq,), dtype=torch.uint8, device=dev)
     if nq:
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(ctx.lib.slm_knn2_filter(ctx.handle, q.data_ptr(), nq, t.data_ptr() if nt else None, nt, int(base),
-                                           num, den, int(bool(cross_check)), idx.data_ptr(), dist.data_ptr(),
-                                           acc.data_ptr(), stream))
+        with ctx.using(variant):
+            _lib.check(ctx.lib.slm_knn2_filter(ctx.handle, q.data_ptr(), nq, t.data_ptr() if nt else None, nt, int(base),
+                                               num, den, int(bool(cross_check)), idx.data_ptr(), dist.data_ptr(),
+                                               acc.data_ptr(), stream))
     return idx, dist, acc
 
 

@@ -3,10 +3,18 @@
 The keyframe-descriptor database (config 5) or the visual vocabulary (config 4) is split into contiguous
 row blocks, one per rank; the query batch is replicated.  Every rank runs the single-GPU kernel on its
 block with ``train_index_base`` = first global row and emits packed top-2 keys
-``(distance << 32) | global index``; ONE all-gather of ``nq x 2`` keys per rank (NCCL over NVLink) is the
-only exchange step, followed by a merge kernel that keeps the two smallest keys -- unsigned key order is
-OpenCV's ``(distance, imgIdx, trainIdx)`` collection order, so the result is byte-identical for any
-shard count.  Frame-to-frame / local-map matching (configs 1-3) never shards.
+``(distance << 32) | global index``; ONE exchange of ``nq x 2`` keys per rank is the only communication step,
+followed by a merge that keeps the two smallest keys -- unsigned key order is OpenCV's
+``(distance, imgIdx, trainIdx)`` collection order, so the result is byte-identical for any shard count.
+Frame-to-frame / local-map matching (configs 1-3) never shards.
+
+Exchanges (``exchange=``):
+  ``nvlink``  peer stores over NVLink / NVSwitch into torch symmetric memory + flags + merge kernel
+              (slm_knn2_exchange: the tensor path's refine kernel is the producer).  Keys travel as 32-bit words
+              ``distance << 16 | index`` when the whole train set has at most 65 536 rows (config 4's vocabulary).
+  ``nccl``    all-gather of the packed keys + slm_merge_top2 (the form north_star names; also the CPU / gloo form).
+  ``a2a``     all-to-all of query slices + per-rank merge + all-gather of the merged results.
+  ``auto``    nvlink when every rank can set it up (the ranks agree through an all-reduce), else nccl.
 
 The reference has no counterpart (loop_closure.py:7-36 matches two frames; place_recognition.py is
 empty): this module only defines how the existing kernel scales.
@@ -29,16 +37,21 @@ def shard_bounds(n_rows: int, world_size: int):
     return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
 
 
+_MAX_NVLINK_WORLD = 16      # kSlmMaxWorld in csrc/slm_internal.cuh
+
+
 class ShardedMatcher:
     """One rank's view of a sharded train set.
 
     ``local_keys(q) -> int64[nq, 2]`` and ``merge(gathered int64[W, nq, 2]) -> result`` default to the CUDA
     entry points (slm_knn2_keys / slm_merge_top2); tests inject CPU stand-ins to exercise the collective
-    plumbing under gloo.
+    plumbing under gloo.  ``total_rows`` = number of train rows over all ranks (an all-reduce at the first query
+    when omitted).
     """
 
     def __init__(self, train_shard, first_row: int, group=None, ratio=(7, 10), variant: Optional[str] = None,
-                 local_keys: Optional[Callable] = None, merge: Optional[Callable] = None, exchange: str = "auto"):
+                 local_keys: Optional[Callable] = None, merge: Optional[Callable] = None, exchange: str = "auto",
+                 total_rows: Optional[int] = None):
         import torch.distributed as dist
         self.train = train_shard
         self.first_row = int(first_row)
@@ -49,15 +62,11 @@ class ShardedMatcher:
         self._merge = merge or self._cuda_merge
         self._variant = variant
         self._gather_bufs = {}
-        # exchange of the per-rank keys: "nccl" = all-gather + merge kernel; "nvlink" = one kernel that stores
-        # the keys straight into every peer's symmetric-memory buffer, flags them and merges (slm_exchange_merge);
-        # "auto" tries nvlink for small query batches and falls back to nccl when peer mapping is unavailable
-        # "a2a" = all-to-all of query slices + all-gather of the merged results: rank r merges only queries
-        # [r * nq / W, (r + 1) * nq / W), so every rank receives ~2 x 16 B x nq instead of 16 B x nq x (W - 1);
-        # (config 4: 1M descriptors -> 28 MB instead of 112 MB per rank at W = 8); opt-in, "auto" never picks it
         if exchange not in ("auto", "nccl", "nvlink", "a2a"):
             raise ValueError("exchange must be auto, nccl, nvlink or a2a")
-        self.exchange = exchange if (exchange == "a2a" or (local_keys is None and merge is None and self.world > 1)) else "nccl"
+        cuda_path = local_keys is None and merge is None and self.world > 1
+        self.exchange = exchange if (exchange == "a2a" or cuda_path) else "nccl"
+        self.total_rows = None if total_rows is None else int(total_rows)
         self._symm = None
         self._step = 0
         self.last_exchange = "none"     # what the last knn2() call actually used
@@ -65,10 +74,7 @@ class ShardedMatcher:
     # -- CUDA implementations ---------------------------------------------------------------------
     def _ctx(self):
         from . import _lib
-        ctx = _lib.context(self.train.device.index or 0)
-        if self._variant is not None:
-            ctx.set_variant(self._variant)
-        return ctx
+        return _lib.context(self.train.device.index or 0)
 
     def _cuda_local_keys(self, q, out=None):
         import torch
@@ -77,8 +83,9 @@ class ShardedMatcher:
         nq, nt = q.shape[0], self.train.shape[0]
         keys = out if out is not None else torch.empty((nq, 2), dtype=torch.int64, device=q.device)
         stream = torch.cuda.current_stream(q.device).cuda_stream
-        _lib.check(ctx.lib.slm_knn2_keys(ctx.handle, q.data_ptr(), nq, self.train.data_ptr() if nt else None, nt,
-                                         self.first_row, keys.data_ptr(), stream))
+        with ctx.using(self._variant):
+            _lib.check(ctx.lib.slm_knn2_keys(ctx.handle, q.data_ptr(), nq, self.train.data_ptr() if nt else None, nt,
+                                             self.first_row, keys.data_ptr(), stream))
         return keys
 
     def _cuda_merge(self, gathered):
@@ -96,17 +103,25 @@ class ShardedMatcher:
                                           dist_.data_ptr(), acc.data_ptr(), stream))
         return idx, dist_, acc
 
-    # -- NVLink exchange ----------------------------------------------------------------------------
-    _NVLINK_MAX_NQ = 8192
+    def _total_rows(self, device):
+        """Train rows over all ranks (selects the exchange's key width; identical on every rank)."""
+        if self.total_rows is None:
+            import torch
+            import torch.distributed as dist
+            n = torch.tensor([int(self.train.shape[0])], dtype=torch.int64, device=device)
+            if self.world > 1:
+                dist.all_reduce(n, group=self.group)
+            self.total_rows = int(n.item())
+        return self.total_rows
 
-    def _symm_setup(self, device):
+    # -- NVLink exchange ----------------------------------------------------------------------------
+    def _symm_setup(self, device, cap):
         """Peer-mapped key buffers + flags through torch symmetric memory (NVLink / NVSwitch P2P)."""
         import ctypes
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = self.group if self.group is not None else dist.group.WORLD
-        cap = self._NVLINK_MAX_NQ
         keys = symm_mem.empty((2, self.world, cap, 2), dtype=torch.int64, device=device)
         flags = symm_mem.empty((2 * self.world,), dtype=torch.int32, device=device)
         flags.zero_()
@@ -118,18 +133,41 @@ class ShardedMatcher:
         self._symm = dict(keys=keys, flags=flags, hk=hk, hf=hf, cap=cap, rank=dist.get_rank(group),
                           key_ptrs=arr(*[int(x) for x in hk.buffer_ptrs]),
                           flag_ptrs=arr(*[int(x) for x in hf.buffer_ptrs]))
+        self._step = 0                                  # fresh flags: the step counter restarts with them
 
     def _nvlink_ready(self, q) -> bool:
-        if self.exchange in ("nccl", "a2a") or not (0 < q.shape[0] <= self._NVLINK_MAX_NQ) or not getattr(q, "is_cuda", False):
+        if self.exchange in ("nccl", "a2a") or q.shape[0] == 0 or not getattr(q, "is_cuda", False):
             return False
-        if self._symm is None:
+        if self.world > _MAX_NVLINK_WORLD:
+            if self.exchange == "nvlink":
+                raise ValueError(f"the NVLink exchange supports at most {_MAX_NVLINK_WORLD} ranks")
+            self.exchange = "nccl"
+            return False
+        nq = int(q.shape[0])
+        if self._symm is None or self._symm["cap"] < nq:
+            # (re)allocate for the larger batch -- nq is the same on every rank, so every rank gets here together.
+            # The ranks then AGREE on the outcome: one that cannot map its peers would otherwise enter the all-gather
+            # while the others wait on flags.
+            import torch
+            import torch.distributed as dist
+            cap = max(2048, 1 << (nq - 1).bit_length())
+            err = None
             try:
-                self._symm_setup(q.device)
-            except Exception as e:              # no peer mapping in this environment
+                if self._symm is not None:
+                    torch.cuda.synchronize(q.device)    # nobody is still reading the old buffers
+                    dist.barrier(group=self.group)
+                self._symm_setup(q.device, cap)
+            except Exception as e:                      # no peer mapping in this environment
+                err = e
+                self._symm = None
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=q.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self._symm = None
                 if self.exchange == "nvlink":
-                    raise
+                    raise RuntimeError(f"NVLink exchange unavailable on at least one rank ({err!r})")
                 import warnings
-                warnings.warn(f"slammatch: NVLink exchange unavailable ({e!r}); using the NCCL all-gather")
+                warnings.warn(f"slammatch: NVLink exchange unavailable ({err!r}); every rank uses the NCCL all-gather")
                 self.exchange = "nccl"
                 return False
         return True
@@ -145,15 +183,24 @@ class ShardedMatcher:
         dist_ = torch.empty((nq, 2), dtype=torch.int32, device=dev)
         acc = torch.empty((nq,), dtype=torch.uint8, device=dev)
         num, den = self.ratio if self.ratio is not None else (0, 1)
+        total = self._total_rows(dev)
         self._step += 1
         nt = self.train.shape[0]
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(ctx.lib.slm_knn2_exchange(ctx.handle, q.data_ptr(), nq, self.train.data_ptr() if nt else None, nt,
-                                             self.first_row, s["cap"], ctypes.cast(s["key_ptrs"], ctypes.c_void_p),
-                                             ctypes.cast(s["flag_ptrs"], ctypes.c_void_p), s["rank"], self.world,
-                                             self._step, int(num), int(den), idx.data_ptr(), dist_.data_ptr(),
-                                             acc.data_ptr(), stream))
+        with ctx.using(self._variant):
+            _lib.check(ctx.lib.slm_knn2_exchange(ctx.handle, q.data_ptr(), nq, self.train.data_ptr() if nt else None, nt,
+                                                 self.first_row, s["cap"], total,
+                                                 ctypes.cast(s["key_ptrs"], ctypes.c_void_p),
+                                                 ctypes.cast(s["flag_ptrs"], ctypes.c_void_p), s["rank"], self.world,
+                                                 self._step, int(num), int(den), idx.data_ptr(), dist_.data_ptr(),
+                                                 acc.data_ptr(), stream))
         return idx, dist_, acc
+
+    def check(self):
+        """Raise if an earlier NVLink exchange on this rank lost a peer (call after synchronising the stream)."""
+        from . import _lib
+        ctx = self._ctx()
+        _lib.check(ctx.lib.slm_exchange_status(ctx.handle))
 
     # -- the sharded query ----------------------------------------------------------------------------
     def _gather(self, keys, slot, async_op=False):
@@ -201,20 +248,19 @@ class ShardedMatcher:
         return idx[:nq], dist_[:nq], acc[:nq]
 
     def knn2(self, q, query_batch: int = 1 << 22):
-        """Local top-2 keys -> all-gather -> merge.  Every rank returns the full, identical result.
+        """Local top-2 keys -> exchange -> merge.  Every rank returns the full, identical result.
 
-        Query sets above ``query_batch`` rows are cut into batches so that the all-gather of batch b (16 bytes
-        per query and rank) overlaps the search of batch b+1.  (Measured on 8 B200s for config 4 the extra
-        launches cost more than the overlap saves, hence the high default.)"""
+        NCCL form: query sets above ``query_batch`` rows are cut into batches so that the all-gather of batch b (16
+        bytes per query and rank) overlaps the search of batch b+1."""
         import torch
         keys_fn, nq = self._local_keys, q.shape[0]
         if self.world == 1:
             keys = keys_fn(q)
             return self._merge(keys.reshape((1,) + tuple(keys.shape)))
         if self._nvlink_ready(q):
-            self.last_exchange = "nvlink peer stores + flags (slm_exchange_merge)"
+            self.last_exchange = "nvlink peer stores + flags (slm_knn2_exchange)"
             return self._knn2_nvlink(q)
-        if self.exchange == "a2a":      # opt-in until measured at 8 GPUs (neutral at 2: 4.71 vs 4.68 ms on c4)
+        if self.exchange == "a2a":
             self.last_exchange = "nccl all-to-all of query slices + all-gather of merged results"
             return self._knn2_a2a(q)
         self.last_exchange = "nccl all-gather"
@@ -244,3 +290,23 @@ class ShardedMatcher:
         pending[1].wait()
         outs.append(self._merge(pending[0]))
         return tuple(torch.cat([o[i] for o in outs], dim=0) for i in range(3))
+
+    def knn2_host(self, q_host, train_host=None):
+        """End-to-end host form of the sharded query: pinned or pageable numpy ``uint8[nq, 32]`` queries in, numpy results
+        out.  ``train_host`` (this rank's rows, optional) re-uploads the shard first -- the form bench.py times as e2e."""
+        import numpy as np
+        import torch
+        dev = self.train.device
+        if train_host is not None:
+            self.train.copy_(torch.from_numpy(train_host) if isinstance(train_host, np.ndarray) else train_host, non_blocking=True)
+        qd = (torch.from_numpy(q_host) if isinstance(q_host, np.ndarray) else q_host).to(dev, non_blocking=True)
+        idx, dist_, acc = self.knn2(qd)
+        nq = idx.shape[0]
+        # one packed read-back: [idx | dist | accept]
+        packed = torch.empty((nq, 17), dtype=torch.uint8, device=dev)
+        packed[:, 0:8] = idx.view(torch.uint8).view(nq, 8)
+        packed[:, 8:16] = dist_.view(torch.uint8).view(nq, 8)
+        packed[:, 16] = acc
+        h = packed.cpu().numpy()
+        return (h[:, 0:8].copy().view(np.int32).reshape(nq, 2), h[:, 8:16].copy().view(np.int32).reshape(nq, 2),
+                h[:, 16].copy())

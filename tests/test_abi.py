@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = slammatch.load()
-    assert lib.slm_version() == 100
+    assert lib.slm_version() == 200
     assert isinstance(lib.slm_last_error(), bytes)
 
 

@@ -1,0 +1,190 @@
+"""Single-GPU loopback of the sharded path's NVLink exchange (slm_knn2_exchange / slm_exchange_merge).
+
+The kernels SCALE_rNN times on 2-8 GPUs -- the refine kernel that stores every query's keys into all peers' buffers and
+publishes the flags, and exchange_wait_merge_kernel that acquires them and merges -- are driven here as W "ranks" on W
+streams of ONE GPU: W contexts, plain CUDA tensors as the peer-mapped key buffers and flag arrays (every "peer
+pointer" is just another tensor on the same device).  Each step runs all ranks' calls back to back, the ranks wait for
+each other only through the flags, and every rank's result must equal the oracle on the full train set, bit for bit,
+for several steps (both buffer halves are reused) and for both key widths.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import slammatch
+from slammatch import _lib, synth
+from slammatch.sharded import shard_bounds
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+class _Ranks:
+    """W loopback ranks on one GPU."""
+
+    def __init__(self, world, cap):
+        import torch
+        old = os.environ.get("SLM_EXCHANGE_MAX_BLOCKS")
+        # few polling blocks per rank: the other ranks' search kernels need whole SMs of the same GPU to make progress
+        os.environ["SLM_EXCHANGE_MAX_BLOCKS"] = "8"
+        try:
+            self.ctxs = [_lib.Context(0) for _ in range(world)]
+        finally:
+            if old is None:
+                del os.environ["SLM_EXCHANGE_MAX_BLOCKS"]
+            else:
+                os.environ["SLM_EXCHANGE_MAX_BLOCKS"] = old
+        self.world, self.cap = world, cap
+        self.streams = [torch.cuda.Stream() for _ in range(world)]
+        self.keys = [torch.zeros((2, world, cap, 2), dtype=torch.int64, device="cuda") for _ in range(world)]
+        self.flags = [torch.zeros((2 * world,), dtype=torch.int32, device="cuda") for _ in range(world)]
+        arr = ctypes.c_uint64 * world
+        self.key_ptrs = arr(*[k.data_ptr() for k in self.keys])
+        self.flag_ptrs = arr(*[f.data_ptr() for f in self.flags])
+        self.step = 0
+        torch.cuda.synchronize()
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+
+    def query(self, q_dev, shards, bounds, total_rows, ratio, variant, fused=True):
+        """One sharded step on all ranks; returns every rank's (idx, dist, acc) as numpy."""
+        import torch
+        nq = q_dev.shape[0]
+        self.step += 1
+        outs = []
+        for r in range(self.world):
+            ctx = self.ctxs[r]
+            idx = torch.full((nq, 2), -9, dtype=torch.int32, device="cuda")
+            dist = torch.full((nq, 2), -9, dtype=torch.int32, device="cuda")
+            acc = torch.full((nq,), 9, dtype=torch.uint8, device="cuda")
+            outs.append((idx, dist, acc))
+            t, (a, b) = shards[r], bounds[r]
+            s = self.streams[r]
+            s.wait_stream(torch.cuda.current_stream())
+            kp = ctypes.cast(self.key_ptrs, ctypes.c_void_p)
+            fp = ctypes.cast(self.flag_ptrs, ctypes.c_void_p)
+            with ctx.using(variant):
+                if fused:
+                    _lib.check(ctx.lib.slm_knn2_exchange(ctx.handle, q_dev.data_ptr(), nq, t.data_ptr() if b > a else None,
+                                                         b - a, a, self.cap, total_rows, kp, fp, r, self.world, self.step,
+                                                         ratio[0], ratio[1], idx.data_ptr(), dist.data_ptr(), acc.data_ptr(),
+                                                         s.cuda_stream))
+                else:
+                    keys = torch.empty((nq, 2), dtype=torch.int64, device="cuda")
+                    _lib.check(ctx.lib.slm_knn2_keys(ctx.handle, q_dev.data_ptr(), nq, t.data_ptr() if b > a else None, b - a,
+                                                     a, keys.data_ptr(), s.cuda_stream))
+                    _lib.check(ctx.lib.slm_exchange_merge(ctx.handle, keys.data_ptr(), nq, self.cap, total_rows, kp, fp, r,
+                                                          self.world, self.step, ratio[0], ratio[1], idx.data_ptr(),
+                                                          dist.data_ptr(), acc.data_ptr(), s.cuda_stream))
+                    outs[-1] = outs[-1] + (keys,)
+        torch.cuda.synchronize()
+        for ctx in self.ctxs:
+            _lib.check(ctx.lib.slm_exchange_status(ctx.handle))
+        return [(o[0].cpu().numpy(), o[1].cpu().numpy(), o[2].cpu().numpy()) for o in outs]
+
+
+def _case(nq, nt, seed):
+    q, t = synth.planted(nq, nt, seed)
+    return q, synth.with_duplicates(t, seed + 1, 0.2)        # exact duplicates across shard boundaries
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("variant", ["auto", "tensor", "popc"])
+def test_loopback_exchange_equals_oracle_64bit_keys(world, variant):
+    """Config 5 in miniature: few queries, long train set (global indices above 65 536 -> 64-bit keys)."""
+    import torch
+    nq, nt = 600, 150_000
+    ranks = _Ranks(world, cap=1024)
+    try:
+        for step in range(5):
+            q, t = _case(nq if step != 3 else 37, nt, 900 + 10 * step)      # a ragged batch in the middle
+            bounds = shard_bounds(nt, world)
+            shards = [torch.from_numpy(t[a:b]).cuda() for a, b in bounds]
+            oi, od = orc.c_knn2(q, t)
+            want = orc.c_ratio(od, 7, 10)
+            res = ranks.query(torch.from_numpy(q).cuda(), shards, bounds, nt, (7, 10), variant)
+            for r, (i, d, a) in enumerate(res):
+                assert np.array_equal(i, oi) and np.array_equal(d, od), (world, variant, step, r)
+                assert np.array_equal(a, want), (world, variant, step, r)
+    finally:
+        ranks.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("variant", ["auto", "tensor"])
+def test_loopback_exchange_config4_regime_32bit_keys(world, variant):
+    """Config 4 in miniature: many queries (above the old 8192 cap), a vocabulary of at most 65 536 words sharded by rows
+    -> compact 32-bit keys (distance << 16 | word), merge kernel with a capped grid."""
+    import torch
+    nq, nt = 20_000, 48_000
+    ranks = _Ranks(world, cap=32768)
+    try:
+        for step in range(3):
+            q, t = _case(nq, nt, 1900 + 10 * step)
+            bounds = shard_bounds(nt, world)
+            shards = [torch.from_numpy(t[a:b]).cuda() for a, b in bounds]
+            oi, od = orc.c_knn2(q, t)
+            res = ranks.query(torch.from_numpy(q).cuda(), shards, bounds, nt, (0, 1), variant)
+            for r, (i, d, a) in enumerate(res):
+                assert np.array_equal(i, oi) and np.array_equal(d, od), (world, variant, step, r)
+                assert a.all()
+    finally:
+        ranks.close()
+
+
+def test_loopback_exchange_merge_entry_point_and_key_widths():
+    """slm_exchange_merge (local keys given; the producer is exchange_store_kernel): same result with compact and with
+    64-bit keys, the per-rank keys equal the oracle's, an empty shard takes part like any other."""
+    import torch
+    world, nq, nt = 4, 3000, 50_000
+    q, t = _case(nq, nt, 77)
+    bounds = [(0, 20_000), (20_000, 20_000), (20_000, 35_008), (35_008, nt)]     # rank 1 holds no rows
+    shards = [torch.from_numpy(t[a:b]).cuda() if b > a else torch.empty((0, 32), dtype=torch.uint8, device="cuda") for a, b in bounds]
+    oi, od = orc.c_knn2(q, t)
+    qd = torch.from_numpy(q).cuda()
+    for total in (nt, 0):                    # 0 = unknown -> 64-bit keys
+        ranks = _Ranks(world, cap=4096)
+        try:
+            for step in range(3):
+                res = ranks.query(qd, shards, bounds, total, (7, 10), "auto", fused=False)
+                for r, (i, d, a) in enumerate(res):
+                    assert np.array_equal(i, oi) and np.array_equal(d, od), (total, step, r)
+                    assert np.array_equal(a, orc.c_ratio(od, 7, 10))
+        finally:
+            ranks.close()
+
+
+def test_lost_peer_is_reported_not_trapped():
+    """A rank whose peers never publish must not hang or poison the CUDA context: the merge kernel gives up after its
+    poll budget, leaves the outputs untouched and the next call reports SLM_ERR_TIMEOUT."""
+    import torch
+    os.environ["SLM_EXCHANGE_MAX_POLLS"] = "2000"
+    try:
+        ranks = _Ranks(2, cap=256)
+    finally:
+        del os.environ["SLM_EXCHANGE_MAX_POLLS"]
+    try:
+        q, t = _case(64, 5000, 5)
+        qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+        ctx = ranks.ctxs[0]
+        idx = torch.full((64, 2), -9, dtype=torch.int32, device="cuda")
+        kp = ctypes.cast(ranks.key_ptrs, ctypes.c_void_p)
+        fp = ctypes.cast(ranks.flag_ptrs, ctypes.c_void_p)
+        _lib.check(ctx.lib.slm_knn2_exchange(ctx.handle, qd.data_ptr(), 64, td.data_ptr(), 2500, 0, 256, 5000, kp, fp, 0, 2, 1,
+                                             7, 10, idx.data_ptr(), None, None, None))       # rank 1 never runs
+        torch.cuda.synchronize()                                                              # returns: no hang, no trap
+        assert (idx.cpu().numpy() == -9).all()
+        with pytest.raises(slammatch.SlamMatchError) as e:
+            _lib.check(ctx.lib.slm_exchange_status(ctx.handle))
+        assert e.value.code == -5 and "rank 1" in str(e.value)
+        _lib.check(ctx.lib.slm_exchange_status(ctx.handle))                                   # the report is cleared
+        # the context is still usable
+        i, d, a = slammatch.knn2(q, t)
+        oi, od = orc.c_knn2(q, t)
+        assert np.array_equal(i, oi) and np.array_equal(d, od)
+    finally:
+        ranks.close()

@@ -14,7 +14,7 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["popc", "tensor", "bmma", "auto"]
+VARIANTS = ["popc", "tensor", "tensor4", "bmma", "auto"]
 
 
 def _variant_available(v):
