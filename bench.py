@@ -232,46 +232,68 @@ def reference_arm(args, w, cfg_id):
 
 
 # ------------------------------------------------------------------------------------------------
-def ours(args, w, cfg_id):
+# parity check outside the timed region: a slice of every rank's output against the C oracle on the FULL train set
+# ------------------------------------------------------------------------------------------------
+def _oracle():
+    from oracle import oracle as orc          # test infrastructure: used here only as the checker
+    orc.build_c()
+    return orc
+
+
+def parity_expected(wl_id, w, cfg_id, q_h, t_full, extra):
+    """rank 0: (query rows checked, expected idx, dist, accept) from oracle/hamming_knn2.c."""
+    orc = _oracle()
+    nq = w["nq"]
+    if wl_id == "c3":
+        desc_h, pairs = extra
+        sel_pairs = sorted({0, len(pairs) // 2, len(pairs) - 1})
+        idx, dist, acc = [], [], []
+        for p in sel_pairs:
+            i, d = orc.c_knn2(desc_h[pairs[p][0]], desc_h[pairs[p][1]])
+            idx.append(i); dist.append(d); acc.append(orc.c_ratio(d, *w["ratio"]))
+        return np.asarray(sel_pairs), np.stack(idx), np.stack(dist), np.stack(acc)
+    if w["cross"] or nq * w["nt"] <= 2_000_000_000 and nq <= 4096:
+        sel = np.arange(nq)                                      # small problems: every query
+    else:
+        n = 64 if nq <= 4096 else 1024
+        sel = np.unique(np.linspace(0, nq - 1, n).astype(np.int64))
+    i, d = orc.c_knn2(q_h[sel], t_full)
+    acc = orc.c_ratio(d, *w["ratio"]) if w["ratio"] else (i[:, 0] >= 0).astype(np.uint8)
+    if w["cross"]:
+        acc = acc & orc.c_cross_check(q_h, t_full, i)
+    return sel, i, d, acc
+
+
+# ------------------------------------------------------------------------------------------------
+def measure(args, wl_id, env, headline):
+    """One workload on the current process group: device-resident value, e2e, roofline, parity check."""
     import torch
     import torch.distributed as dist
     import slammatch
     from slammatch import _lib
     from slammatch.sharded import ShardedMatcher, shard_bounds
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        # NCCL prints its version banner on stdout, and honours NCCL_DEBUG_FILE only above the VERSION level: raise the
-        # level to WARN and send the log to stderr so that the JSON line is the only thing on stdout
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, local, dev, ctx, peaks = env["rank"], env["world"], env["local"], env["dev"], env["ctx"], env["peaks"]
+    w = WORKLOADS[wl_id]
+    cfg_id = int(wl_id[1]) + (5 if wl_id[0] == "h" else 0)
+    steps = args.steps if headline else max(3, min(args.steps, args.config_steps))
+    e2e_steps = max(1, min(steps, args.e2e_steps if headline else 2))
     sharded = w["sharded"] and world > 1
-    if world > 1 and not w["sharded"]:
-        # path does not shard: independent replicas
-        pass
-
-    ctx = _lib.context(local)
-    ctx.set_variant(args.variant)
     nq, nt = w["nq"], w["nt"]
     num, den = w["ratio"] if w["ratio"] else (0, 1)
+    ctx.set_variant(args.variant)
 
     # ---- inputs (host, pinned) and device-resident copies ----------------------------------------
     first, last = shard_bounds(nt, world)[rank] if sharded else (0, nt)
-    if args.workload == "c3":
+    extra = None
+    if wl_id == "c3":
         frames = w["frames"]
         base = queries(cfg_id, nq, nq)
         rng = np.random.default_rng(3000)
         desc_h = np.stack([base ^ np.packbits(rng.random((nq, 256)) < 0.02 * (1 + f % 5), axis=1, bitorder="little")
                            for f in range(frames)])
         pairs = np.array([(i, j) for i in range(frames) for j in range(i + 1, frames)], dtype=np.int32)
+        extra = (desc_h, pairs)
         desc_pin = torch.from_numpy(desc_h).pin_memory()
         desc_d = desc_pin.to(dev)
         P = pairs.shape[0]
@@ -280,6 +302,7 @@ def ours(args, w, cfg_id):
         acc_d = torch.empty((P, nq), dtype=torch.uint8, device=dev)
         cmp_per_step = float(P) * nq * nq
         in_bytes = desc_h.nbytes
+        q_h = t_h = None
     else:
         q_h = queries(cfg_id, nq, nt)
         t_h = train_rows(cfg_id, first, last)
@@ -289,11 +312,11 @@ def ours(args, w, cfg_id):
         t_d = t_pin.to(dev)
         cmp_per_step = float(nq) * nt            # whole job, all ranks together
         in_bytes = q_h.nbytes + t_h.nbytes
-        sm = ShardedMatcher(t_d, first, ratio=w["ratio"], variant=args.variant, exchange=args.exchange)
+        sm = ShardedMatcher(t_d, first, ratio=w["ratio"], variant=args.variant, exchange=args.exchange, total_rows=nt)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def step_device():
-        if args.workload == "c3":
+        if wl_id == "c3":
             _lib.check(ctx.lib.slm_knn2_batched(ctx.handle, desc_d.data_ptr(), frames, nq, pairs.ctypes.data, P, num, den,
                                                 idx_d.data_ptr(), dist_d.data_ptr(), acc_d.data_ptr(), stream))
             return idx_d, dist_d, acc_d
@@ -304,7 +327,9 @@ def ours(args, w, cfg_id):
     # L2 hygiene: inputs larger than L2 stream from HBM every step; smaller workloads get an L2 flush
     flush = None
     if in_bytes < 2 * L2_BYTES:
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        flush = env.get("flush")
+        if flush is None:
+            flush = env["flush"] = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -322,9 +347,11 @@ def ours(args, w, cfg_id):
 
     # ---- timed region: device-resident inputs, CUDA events on the launching stream -----------------
     ctx.profile(True)
-    ctx.profile_read()
-    launches0 = ctx.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    try:
+        ctx.profile_read()
+    except Exception:
+        pass
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 2)]
     barrier()
     sampler.reset()
     # one more untimed step queued directly in front of the start event: the barrier above idles the GPU for
@@ -334,66 +361,111 @@ def ours(args, w, cfg_id):
     launches0 = ctx.launch_count()
     wall0 = time.perf_counter()
     if flush is None:
-        evs[0][0].record()
-        for _ in range(args.steps):
+        evs[0].record()
+        for k in range(steps):
             out = step_device()
-        evs[0][1].record()
-        sampler.sample_now()          # the GPU is still working through the queued steps here
+            evs[k + 1].record()            # also the start of step k + 1: per-step times for min / median
+        sampler.sample_now()              # the GPU is still working through the queued steps here
         barrier()
-        dev_ms = evs[0][0].elapsed_time(evs[0][1])
+        dev_ms = evs[0].elapsed_time(evs[steps])
+        per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(steps)]
     else:
-        for k in range(args.steps):
+        for k in range(steps):
             flush.fill_(k & 0xFF)
-            evs[k][0].record()
+            evs[2 * k].record()
             out = step_device()
-            evs[k][1].record()
+            evs[2 * k + 1].record()
         barrier()
-        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        per_step = [evs[2 * k].elapsed_time(evs[2 * k + 1]) for k in range(steps)]
+        dev_ms = sum(per_step)
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop()
     kern_ms, kern_n = ctx.profile_read()
     ctx.profile(False)
     launches = ctx.launch_count() - launches0
+    variant = ctx.last_variant()
+    kernel_name = ctx.last_kernel()
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     dev_ms = float(t_ms.item())
     jobs = world if (world > 1 and not w["sharded"]) else 1     # replicas: N independent copies of the job
-    value = cmp_per_step * jobs * args.steps / (dev_ms * 1e-3) / 1e9
+    value = cmp_per_step * jobs * steps / (dev_ms * 1e-3) / 1e9
     matched = int(out[2].sum().item())
+
+    # ---- parity: a slice of THIS rank's output of the timed path against the oracle on the full train set ----
+    parity = None
+    if not args.no_parity:
+        n_sel = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            t_full = t_h if (wl_id == "c3" or not sharded) else train_rows(cfg_id, 0, nt)
+            sel, e_i, e_d, e_a = parity_expected(wl_id, w, cfg_id, q_h, t_full, extra)
+            del t_full
+            n_sel[0] = sel.shape[0]
+        if world > 1:
+            dist.broadcast(n_sel, 0)
+        n = int(n_sel.item())
+        shape_i = (n, nq, 2) if wl_id == "c3" else (n, 2)
+        shape_a = (n, nq) if wl_id == "c3" else (n,)
+        if rank == 0:
+            sel_t = torch.from_numpy(np.ascontiguousarray(sel, dtype=np.int64)).to(dev)
+            e_i_t, e_d_t = torch.from_numpy(e_i).to(dev), torch.from_numpy(e_d).to(dev)
+            e_a_t = torch.from_numpy(np.ascontiguousarray(e_a, dtype=np.uint8)).to(dev)
+        else:
+            sel_t = torch.empty((n,), dtype=torch.int64, device=dev)
+            e_i_t = torch.empty(shape_i, dtype=torch.int32, device=dev)
+            e_d_t = torch.empty(shape_i, dtype=torch.int32, device=dev)
+            e_a_t = torch.empty(shape_a, dtype=torch.uint8, device=dev)
+        if world > 1:
+            for x in (sel_t, e_i_t, e_d_t, e_a_t):
+                dist.broadcast(x, 0)
+        ok = bool(torch.equal(out[0][sel_t], e_i_t) and torch.equal(out[1][sel_t], e_d_t) and torch.equal(out[2][sel_t], e_a_t))
+        ok_t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        parity = {"queries": (n * nq if wl_id == "c3" else n), "ok": bool(ok_t.item()), "ranks_checked": world,
+                  "against": "oracle/hamming_knn2.c on the full train set (idx, dist, accept of the timed path's output)"}
 
     # ---- e2e: the public host-buffer call, H2D and D2H inside the timed region ---------------------
     def step_e2e():
-        if args.workload == "c3":
+        if wl_id == "c3":
             desc_d.copy_(desc_pin, non_blocking=True)
             step_device()
             return idx_d.cpu(), dist_d.cpu(), acc_d.cpu()
         if sharded:
-            q_d.copy_(q_pin, non_blocking=True)
-            t_d.copy_(t_pin, non_blocking=True)
-            i, d, a = sm.knn2(q_d)
-            return i.cpu(), d.cpu(), a.cpu()
+            return sm.knn2_host(q_pin.numpy(), train_host=t_pin)
         return slammatch.knn2(q_pin.numpy(), t_pin.numpy(), ratio=w["ratio"], cross_check=w["cross"], device=local)
 
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_val = cmp_per_step * jobs * e2e_steps / float(t_e.item()) / 1e9
-    out_bytes = (P * nq if args.workload == "c3" else nq) * 17
+    def time_e2e(fn, n):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize(dev)
+        t_e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        return cmp_per_step * jobs * n / float(t_e.item()) / 1e9
+
+    e2e_val = time_e2e(step_e2e, e2e_steps)
+    out_bytes = (P * nq if wl_id == "c3" else nq) * 17
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
+           "steps": e2e_steps,
+           "api": ("slammatch.knn2(pinned host arrays) -> slm_knn2_host" if not (sharded or wl_id == "c3") else
+                   "ShardedMatcher.knn2_host(host queries, host shard)" if sharded else
+                   "pinned host -> device copy + slm_knn2_batched + result read-back")}
+    if world == 1 and wl_id != "c3":
+        # the drop-in caller hands PAGEABLE numpy arrays (orb.py:23-24): same call, inputs not pinned
+        q_pg, t_pg = q_h.copy(), t_h.copy()
+        e2e["pageable"] = {"value": time_e2e(lambda: slammatch.knn2(q_pg, t_pg, ratio=w["ratio"], cross_check=w["cross"],
+                                                                     device=local), e2e_steps), "unit": UNIT}
+        del q_pg, t_pg
 
     # The object-level drop-in call the unmodified reference makes (tracking.py:22): matcher.knnMatch(des1, des2, k=2)
     # returning tuples of cv2.DMatch -- same copies as e2e plus the construction of 2 * nq result objects.
-    matcher_line = None
-    if world == 1 and args.workload in ("c1", "c2"):
+    if world == 1 and wl_id in ("c1", "c2"):
         m = slammatch.Matcher(crossCheck=False, device=local)
         qn, tn = q_pin.numpy(), t_pin.numpy()
         for _ in range(2):
@@ -402,107 +474,144 @@ def ours(args, w, cfg_id):
         for _ in range(e2e_steps):
             rows = m.knnMatch(qn, tn, k=2)
         dt = (time.perf_counter() - t0) / e2e_steps
-        matcher_line = {"value": cmp_per_step / dt / 1e9, "unit": UNIT, "us_per_call": dt * 1e6, "rows": len(rows),
-                        "api": "slammatch.Matcher().knnMatch(des1, des2, k=2) -> tuple[nq] of tuple[2] of cv2.DMatch"}
+        e2e["matcher_knnMatch"] = {"value": cmp_per_step / dt / 1e9, "unit": UNIT, "us_per_call": dt * 1e6, "rows": len(rows),
+                                   "api": "slammatch.Matcher().knnMatch(des1, des2, k=2) -> tuple[nq] of tuple[2] of cv2.DMatch"}
 
     # Same call with the train set held in a persistent device-resident collection (OpenCV's matcher.add([...]) +
     # knnMatch(q, k) form; slammatch.KeyframeDB): the DB is uploaded once, outside the timed region, and every step
     # moves only the query descriptors in and the results out.  Reported NEXT TO e2e, never instead of it.
-    resident = None
-    if world == 1 and args.workload in ("c5", "c4"):
+    if world == 1 and wl_id in ("c5", "c4"):
         db = slammatch.KeyframeDB(device=local, capacity=nt)
         db.add(t_d)
         qn = q_pin.numpy()
-        for _ in range(2):
-            db.query(qn, ratio=w["ratio"])
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            db.query(qn, ratio=w["ratio"])
-        torch.cuda.synchronize(dev)
-        resident = {"value": cmp_per_step * e2e_steps / (time.perf_counter() - t0) / 1e9, "unit": UNIT,
-                    "h2d_bytes_per_step": int(q_h.nbytes), "d2h_bytes_per_step": int(out_bytes),
-                    "api": "slammatch.KeyframeDB.add(train) once, then .query(host queries) per step"}
+        e2e["resident_db"] = {"value": time_e2e(lambda: db.query(qn, ratio=w["ratio"]), e2e_steps), "unit": UNIT,
+                              "h2d_bytes_per_step": int(q_h.nbytes), "d2h_bytes_per_step": int(out_bytes),
+                              "api": "slammatch.KeyframeDB.add(train) once, then .query(host queries) per step"}
         del db
 
-    if rank == 0:
-        peaks = {}
+    # ---- roofline of the dominant kernel, against ceilings measured now, in this process ----------------
+    per_rank_cmp = cmp_per_step / (world if sharded else 1)
+    kern_avg_ms = kern_ms / max(kern_n, 1)
+    kernels_per_step = max(kern_n // (steps + 1), 1)   # the profile also holds the ramp step
+    cmp_per_launch = per_rank_cmp / kernels_per_step
+    popc_tcmp, popc_lanes = ctx.probe_popc_peak(3)
+    roof = {"kernel": kernel_name, "kernel_ms": kern_avg_ms, "traffic": None}
+    if variant in ("tensor", "tensor4"):
+        kind = "mxf4" if variant == "tensor4" else "f8f6f4"
+        tf_probe, mac_probe = ctx.probe_tensor_peak(kind, 4096, 5)
+        ach = cmp_per_launch * 512 / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
+        bf16 = peaks.get("bf16_tflops")
+        roof.update({"bound": "tensor", "achieved": ach, "peak": tf_probe, "unit": "TFLOP/s",
+                     "frac": (ach / tf_probe) if ach else None,
+                     "peak_note": ("tcgen05.mma kind::%s ceiling measured in this process right after the timed region "
+                                   "(slm_probe_tensor_peak: back-to-back MMAs from shared memory on every SM, best of 5 launches; "
+                                   "%.0f MAC/clk/SM by clock64); MEASURED_PEAKS.json has no fp8/fp4 entry (cuBLAS bf16 burst %s TF/s)"
+                                   % (kind, mac_probe, bf16)),
+                     "mac_per_clk_per_sm_probe": mac_probe,
+                     "frac_vs_2x_bf16_measured": (ach / (2.0 * bf16)) if (ach and bf16) else None,
+                     "algorithmic_unit": "1 cmp = 512 flop on the tensor pipe (256-term +-1 dot product) = 8 POPC32 on the integer pipe"})
+    elif kernel_name == "knn2_stream_kernel":
+        alg_bytes = 32.0 * (nq + nt / (world if sharded else 1)) + 16.0 * nq
+        ach = alg_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else None
+        peak = peaks.get("hbm_gbs", 6650.0)
+        roof.update({"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                     "peak_note": ("measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s"),
+                     "algorithmic_bytes": alg_bytes})
+    elif variant == "bmma":
+        ach = cmp_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
+        roof.update({"bound": "issue_slots(b1 mma.sync emulation)", "achieved": ach, "peak": None, "unit": "Tcmp/s", "frac": None,
+                     "peak_note": "no native b1 tensor instruction on sm_100a; see profiles/r1_ncu_bmma_c5.txt"})
+    else:
+        ach = cmp_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
+        roof.update({"bound": "int_popc(xu pipe)", "achieved": ach, "peak": popc_tcmp, "unit": "Tcmp/s",
+                     "frac": (ach / popc_tcmp) if ach else None,
+                     "peak_note": "variant P's comparison loop on every SM, measured in this process (slm_probe_popc_peak)"})
+    # the ALGORITHMIC integer roofline SURVEY.md section 8(d) names (8 POPC32 per comparison), whatever pipe the kernel used
+    roof["popc_algorithmic_peak_tcmp_s"] = popc_tcmp
+    roof["popc_lanes_per_clk_per_sm_probe"] = popc_lanes
+    kernel_tcmp = cmp_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
+    roof["frac_vs_popc_algorithmic"] = (kernel_tcmp / popc_tcmp) if (kernel_tcmp and popc_tcmp) else None
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            ent = json.load(open(tr)).get(roof["kernel"], {}).get(wl_id)
+            if isinstance(ent, dict):
+                roof["traffic"], roof["traffic_source"] = ent.get("bytes"), ent.get("source")
         except Exception:
             pass
-        variant = ctx.last_variant()
-        kernel_name = ctx.last_kernel()
-        per_rank_cmp = cmp_per_step / (world if sharded else 1)
-        kern_avg_ms = kern_ms / max(kern_n, 1)
-        kernels_per_step = max(kern_n // (args.steps + 1), 1)   # the profile also holds the ramp step
-        cmp_per_launch = per_rank_cmp / kernels_per_step
-        if variant == "tensor":
-            # one comparison = a 256-term dot product of +-1 fp8 values = 512 flop on the tcgen05 pipe
-            ach = cmp_per_launch * 512 / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
-            bf16 = peaks.get("bf16_tflops", 1590.0)
-            probe = {}
-            try:
-                probe = json.load(open(os.path.join(ROOT, "profiles", "peaks_probe.json")))
-            except Exception:
-                pass
-            # The kernel issues tcgen05.mma kind::f8f6f4.  MEASURED_PEAKS.json only holds a cuBLAS bf16 figure,
-            # so the denominator is the tensor pipe's own fp8 ceiling: this repo's back-to-back tcgen05 probe
-            # measured 8191 MAC/clk/SM (profiles/r1_tc_probe_v2.txt) = the architectural 8192; times 2 flop,
-            # the SM count and the MAX SM clock (an upper bound: the kernel cannot clock higher), or 2 x the
-            # measured bf16 figure if that is larger.
-            macs = probe.get("tcgen05_f8f6f4_mac_per_clk_per_sm", 8192)
-            clk_mhz = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            peak = max(2.0 * bf16, macs * 2.0 * sms * clk_mhz * 1e6 / 1e12)
-            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None,
-                    "kernel": kernel_name or "knn2_tc2_kernel", "kernel_ms": kern_avg_ms,
-                    "peak_note": ("max(2 x measured cuBLAS bf16 burst %.1f TF/s [%s], tcgen05 kind::f8f6f4 ceiling = %d MAC/clk/SM "
-                                  "(own probe) x 2 x %d SMs x %.0f MHz max SM clock)"
-                                  % (bf16, "MEASURED_PEAKS.json" if peaks else "fallback", macs, sms, clk_mhz)),
-                    "frac_vs_2x_bf16_measured": (ach / (2.0 * bf16)) if ach else None,
-                    "algorithmic_unit": "1 cmp = 512 fp8 flop (256-bit +-1 dot product)"}
-        elif kernel_name == "knn2_stream_kernel":
-            # nq <= 8 runs knn2_stream_kernel: the train set streams through the SMs once
-            alg_bytes = 32.0 * (nq + nt / (world if sharded else 1)) + 16.0 * nq
-            ach = alg_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else None
-            peak = peaks.get("hbm_gbs", 6650.0)
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                    "traffic": None, "kernel": "knn2_stream_kernel", "kernel_ms": kern_avg_ms,
-                    "peak_note": ("measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s"),
-                    "algorithmic_bytes": alg_bytes}
-        elif variant == "bmma":
-            # b1 mma.sync is emulated by ptxas on sm_100a (8 IMMA + ~100 logic/move instructions per MMA): the
-            # kernel is issue-slot-bound (ncu: issue active 70 %, legacy tensor pipe 30 %), no single pipe peak applies
-            ach = cmp_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
-            roof = {"bound": "issue_slots(b1 mma.sync emulation)", "achieved": ach, "peak": None, "unit": "Tcmp/s",
-                    "frac": None, "traffic": None, "kernel": "knn2_bmma_kernel", "kernel_ms": kern_avg_ms,
-                    "peak_note": "no native b1 tensor instruction on sm_100a; see profiles/r1_ncu_bmma_c5.txt"}
-        else:
-            # integer pipe: 8 POPC32 per comparison on the XU pipe; measured 15.8 lanes/clk/SM (profiles/r1_pipe_rates.txt)
-            probe = {}
-            try:
-                probe = json.load(open(os.path.join(ROOT, "profiles", "peaks_probe.json")))
-            except Exception:
-                pass
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            popc_rate = probe.get("popc32_lanes_per_clk_per_sm", 16.0) * sms * (clocks.get("sm_max_mhz") or 1965.0) * 1e6
-            ach = cmp_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else None
-            peak = popc_rate / 8 / 1e12
-            roof = {"bound": "int_popc(xu pipe)", "achieved": ach, "peak": peak, "unit": "Tcmp/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None, "kernel": kernel_name or "knn2_popc_kernel",
-                    "kernel_ms": kern_avg_ms,
-                    "peak_note": "measured POPC32 lanes/clk/SM (own probe) x SMs x max SM clock / 8 POPC per cmp"}
-        tr = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr):
-            try:
-                roof["traffic"] = json.load(open(tr)).get(roof["kernel"], {}).get(args.workload)
-            except Exception:
-                pass
 
+    res = {
+        "workload": w["name"], "value": value, "unit": UNIT, "steps": steps, "ms_per_step": dev_ms / steps,
+        "ms_min": float(np.min(per_step)), "ms_median": float(np.median(per_step)),
+        "variant": variant, "nq": nq, "nt": nt,
+        "l2": "inputs larger than L2 (streamed from HBM every step)" if flush is None else "256 MiB L2 flush between timed steps",
+        "parallelism": (f"train rows sharded over {world} ranks, exchange of packed top-2 keys ({sm.last_exchange}) + merge"
+                        if sharded else ("single GPU" if world == 1 else f"{world} replicas")),
+        "scaling": "strong" if w["sharded"] else "replicas",
+        "matched_per_step": matched, "matched_queries_per_s": matched * jobs / (dev_ms / steps * 1e-3),
+        "wall_ms_per_step": wall_ms / steps, "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": e2e, "roofline": roof, "parity_check": parity,
+    }
+    # release this workload's device memory before the next one
+    del out
+    torch.cuda.empty_cache()
+    return res
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from slammatch import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        # NCCL prints its version banner on stdout, and honours NCCL_DEBUG_FILE only above the VERSION level: raise the
+        # level to WARN and send the log to stderr so that the JSON line is the only thing on stdout
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    env = dict(rank=rank, world=world, local=local, dev=dev, ctx=_lib.context(local), peaks=peaks)
+
+    head = measure(args, args.workload, env, headline=True)
+    # every other BASELINE config rides in the same line: all of them on one GPU, the sharded ones (c4) under torchrun
+    if args.configs == "auto":
+        others = [c for c in ("c4", "c3", "c2", "c1", "h1") if c != args.workload] if world == 1 else \
+                 [c for c in ("c4", "c5") if c != args.workload]
+    elif args.configs == "none":
+        others = []
+    else:
+        others = [c for c in args.configs.split(",") if c and c != args.workload]
+    configs = {}
+    for c in others:
+        r = measure(args, c, env, headline=False)
+        configs[c] = {k: r[k] for k in ("workload", "value", "unit", "steps", "ms_per_step", "ms_min", "ms_median", "variant",
+                                        "parallelism", "scaling", "gpu_launches", "clocks", "parity_check")}
+        configs[c]["kernel"] = r["roofline"]["kernel"]
+        configs[c]["kernel_ms"] = r["roofline"]["kernel_ms"]
+        configs[c]["roofline_frac"] = r["roofline"].get("frac")
+        configs[c]["roofline_bound"] = r["roofline"].get("bound")
+        configs[c]["frac_vs_popc_algorithmic"] = r["roofline"].get("frac_vs_popc_algorithmic")
+        configs[c]["e2e"] = {k: v for k, v in r["e2e"].items() if k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step",
+                                                                          "pageable", "matcher_knnMatch")}
+
+    bad = [c for c, r in [(args.workload, head)] + list(configs.items()) if r["parity_check"] and not r["parity_check"]["ok"]]
+    if rank == 0:
+        w = WORKLOADS[args.workload]
         cpu = None
         if world == 1 and not args.no_cpu:
+            cfg_id = int(args.workload[1]) + (5 if args.workload[0] == "h" else 0)
             run, kind, desc, cores, qs, ts = cpu_sample(w, cfg_id, target_s=12.0)
             t0 = time.perf_counter()
             run(qs, ts)
@@ -510,34 +619,29 @@ def ours(args, w, cfg_id):
             cpu = {"value": qs.shape[0] * ts.shape[0] / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": f"{qs.shape[0]} queries x first {ts.shape[0]} train rows, one pass ({dt:.1f} s)",
                    "matcher": desc}
-
+        variant = head["variant"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if w["sharded"] else "replicas", "vs_baseline": None,
-            "dtype": "e4m3(+-1 bits), f32 accumulate (exact)" if variant == "tensor" else "u32",
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": head["steps"],
+            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "ms_min": head["ms_min"],
+            "ms_median": head["ms_median"], "higher_is_better": True,
+            "scaling": head["scaling"], "vs_baseline": None,
+            "dtype": {"tensor4": "e2m1(+-1 bits, UE8M0 scales 1.0), f32 accumulate (exact)",
+                      "tensor": "e4m3(+-1 bits), f32 accumulate (exact)"}.get(variant, "u32"),
             "data": "synthetic",
-            "config": {"workload": w["name"], "nq": nq, "nt": nt, "variant": variant, "variant_requested": args.variant,
-                       "l2": "inputs larger than L2 (streamed from HBM every step)" if flush is None
-                             else "256 MiB L2 flush between timed steps",
-                       "parallelism": (f"train rows sharded over {world} ranks, exchange of packed top-2 keys ({sm.last_exchange}) + merge"
-                                       if sharded else ("single GPU" if world == 1 else f"{world} replicas"))},
-            "matched_queries_per_s": matched * jobs / (dev_ms / args.steps * 1e-3),
-            "matched_per_step": matched,
-            "wall_ms_per_step": wall_ms / args.steps,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
-                    "steps": e2e_steps, "api": "slammatch.knn2(host arrays) -> slm_knn2_host" if not (sharded or args.workload == "c3")
-                    else "pinned host -> device copy + device entry points + result read-back",
-                    "resident_db": resident, "matcher_knnMatch": matcher_line},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": roof,
-            "cpu_baseline": cpu,
+            "config": {"workload": head["workload"], "nq": head["nq"], "nt": head["nt"], "variant": variant,
+                       "variant_requested": args.variant, "l2": head["l2"], "parallelism": head["parallelism"]},
+            "matched_queries_per_s": head["matched_queries_per_s"], "matched_per_step": head["matched_per_step"],
+            "wall_ms_per_step": head["wall_ms_per_step"],
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+            "roofline": head["roofline"], "cpu_baseline": cpu, "parity_check": head["parity_check"],
+            "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if bad:
+        raise SystemExit(f"parity check FAILED for {bad}: the GPU result differs from the oracle")
 
 
 def main():
@@ -547,18 +651,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="auto", choices=["auto", "popc", "tensor", "bmma"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "popc", "tensor", "tensor4", "bmma"])
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--configs", default="auto",
+                    help="other BASELINE configs measured briefly after the headline workload and reported under 'configs': "
+                         "auto (1 GPU: c4,c3,c2,c1,h1; torchrun: the sharded c4), none, or a comma list")
+    ap.add_argument("--config-steps", type=int, default=10, help="timed steps of each entry under 'configs'")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvlink", "a2a"],
                     help="sharded path: how per-rank keys are exchanged (auto = NVLink peer stores when available)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check of the timed path's output")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
-    cfg_id = int(args.workload[1]) + (5 if args.workload[0] == "h" else 0)
     if args.impl == "reference":
+        w = WORKLOADS[args.workload]
+        cfg_id = int(args.workload[1]) + (5 if args.workload[0] == "h" else 0)
         reference_arm(args, w, cfg_id)
     else:
-        ours(args, w, cfg_id)
+        ours(args)
 
 
 if __name__ == "__main__":

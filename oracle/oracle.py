@@ -181,6 +181,16 @@ def find_2d_3d_restated(des_i, kp_i, kp_i1_pts, des_i1, pts3d, max_distance=1000
     return q2, Q1, q1
 
 
+def stereo_matches_restated(kp_left_pts, des_left, kp_right_pts, des_right, knn=np_knn2):
+    """keypoint.py:35-57 up to the fundamental-matrix step: ratio 0.7 and the four gathers (left / right keypoint
+    coordinates, left / right descriptors of the good matches)."""
+    idx, dist = knn(des_left, des_right)
+    rows = good_rows(idx, dist)
+    tr = idx[rows, 0]
+    return (np.asarray(kp_left_pts)[rows].reshape(-1, 2), np.asarray(kp_right_pts)[tr].reshape(-1, 2),
+            np.asarray(des_left)[rows].reshape(-1, 32), np.asarray(des_right)[tr].reshape(-1, 32))
+
+
 # ----------------------------------------------------------------------------------------------
 # C restatement (oracle/hamming_knn2.c)
 # ----------------------------------------------------------------------------------------------

@@ -230,6 +230,11 @@ int slm_create(int device, slm_ctx **ctx_out)
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming));
     SLM_CUDA(cudaEventCreateWithFlags(&ctx->last_ev, cudaEventDisableTiming));
+    // last-block-done counter of the frame kernel and the exchange producers: zeroed HERE, synchronously -- a lazy
+    // cudaMemset on the legacy stream is not ordered with kernels on the caller's non-blocking streams
+    SLM_CUDA(cudaMalloc(&ctx->done_counter, sizeof(unsigned)));
+    SLM_CUDA(cudaMemset(ctx->done_counter, 0, sizeof(unsigned)));
+    SLM_CUDA(cudaDeviceSynchronize());
     *ctx_out = ctx;
     return SLM_OK;
 }

@@ -106,10 +106,6 @@ __global__ void __launch_bounds__(256) exchange_wait_merge_kernel(slm_exchange e
 int slm_exchange_setup(slm_ctx *ctx, slm_exchange *ex, const uint64_t *peer_keys_host, const uint64_t *peer_flags_host,
                        int32_t rank, int32_t world, uint32_t step, int64_t cap, int64_t nt_global)
 {
-    if (!ctx->done_counter) {
-        SLM_CUDA(cudaMalloc(&ctx->done_counter, sizeof(unsigned)));
-        SLM_CUDA(cudaMemset(ctx->done_counter, 0, sizeof(unsigned)));
-    }
     if (!ctx->exchange_status) {
         // mapped pinned host memory: the merge kernel reports a lost peer here, the next API call reads it
         SLM_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->exchange_status), 4 * sizeof(int), cudaHostAllocMapped));
@@ -146,7 +142,7 @@ int slm_exchange_wait_merge(slm_ctx *ctx, const slm_exchange &ex, int64_t nq, in
     if (blocks < 1) blocks = 1;
     int *status_dev = nullptr;
     SLM_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&status_dev), ctx->exchange_status, 0));
-    SLM_CUDA(slm_launch(exchange_wait_merge_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, /*pdl=*/true, ex, (long long)nq,
+    SLM_CUDA(slm_launch(exchange_wait_merge_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, /*pdl=*/!ctx->no_pdl, ex, (long long)nq,
                         (int)ratio_num, (int)ratio_den, idx_out, dist_out, accept_out, ctx->exchange_max_polls,
                         (volatile int *)status_dev));
     ctx->launches += 1;

@@ -332,10 +332,6 @@ static int frame_run(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t
         }
         SLM_TRY(slm_buf_reserve(ctx, &ctx->rev, (size_t)nt * 16));
         p.rev_keys = reinterpret_cast<unsigned long long *>(ctx->rev.p);
-        if (!ctx->done_counter) {
-            SLM_CUDA(cudaMalloc(&ctx->done_counter, sizeof(unsigned)));
-            SLM_CUDA(cudaMemset(ctx->done_counter, 0, sizeof(unsigned)));
-        }
         p.done_counter = ctx->done_counter;
     }
     if (items > 0x7FFFFFFFll) return slm_fail(SLM_ERR_UNSUPPORTED, "problem too large for one launch");

@@ -326,13 +326,11 @@ def get_matches(kp1_pts, des1, kp2_pts, des2, device: int = 0):
     return q1, q2
 
 
-def get_matches_device(kp1_xy, des1, kp2_xy, des2, ratio=REFERENCE_RATIO):
-    """tracking.get_matches (tracking.py:12-34) with everything device-resident: descriptors ``uint8[n,32]`` and
-    keypoint coordinates ``float32[n,2]`` are CUDA tensors; the search, the ratio loop (with its truncation at the
-    first short row), the compaction of ``good`` and both gathers run on the GPU.  Returns ``(q1, q2)`` CUDA
-    tensors ``float32[M,2]`` -- one 4-byte read-back (M) is the only host synchronisation."""
+def _compact_and_gather(idx, dist, acc, gathers):
+    """Device-side tail shared by the three reference helpers: ordered compaction of the accepted rows (with the
+    truncation at the first short row, tracking.py:25-30) + one slm_gather_rows per ``(column, tensor)`` in ``gathers``
+    (column 0 gathers by queryIdx, 1 by trainIdx).  One 4-byte read-back (the match count) is the only host sync."""
     import torch
-    idx, dist, acc = knn2(des1, des2, ratio=ratio)
     dev, nq = idx.device, idx.shape[0]
     ctx = _lib.context(dev.index or 0)
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -341,13 +339,61 @@ def get_matches_device(kp1_xy, des1, kp2_xy, des2, ratio=REFERENCE_RATIO):
     _lib.check(ctx.lib.slm_compact_matches(ctx.handle, idx.data_ptr(), dist.data_ptr(), acc.data_ptr(), nq, 1,
                                            matches.data_ptr(), count.data_ptr(), stream))
     out = []
-    for col, xy in ((0, kp1_xy), (1, kp2_xy)):
-        xy = xy.contiguous()
-        if xy.dtype != torch.float32 or xy.dim() != 2:
-            raise ValueError("keypoint coordinates must be float32[n, k] CUDA tensors")
-        o = torch.empty((max(nq, 1), xy.shape[1]), dtype=torch.float32, device=dev)
-        _lib.check(ctx.lib.slm_gather_rows(ctx.handle, xy.data_ptr(), 4 * xy.shape[1], matches.data_ptr(),
-                                           count.data_ptr(), nq, col, o.data_ptr(), stream))
+    for col, src in gathers:
+        src = src.contiguous()
+        if src.dim() != 2 or not src.is_cuda:
+            raise ValueError("gather sources must be 2-D CUDA tensors")
+        row_bytes = src.shape[1] * src.element_size()
+        if row_bytes % 4:
+            raise ValueError("gather rows must be a multiple of 4 bytes")
+        o = torch.empty((max(nq, 1), src.shape[1]), dtype=src.dtype, device=dev)
+        _lib.check(ctx.lib.slm_gather_rows(ctx.handle, src.data_ptr(), row_bytes, matches.data_ptr(), count.data_ptr(), nq,
+                                           col, o.data_ptr(), stream))
         out.append(o)
     m = int(count.item())
-    return out[0][:m], out[1][:m]
+    return [o[:m] for o in out]
+
+
+def get_matches_device(kp1_xy, des1, kp2_xy, des2, ratio=REFERENCE_RATIO):
+    """tracking.get_matches (tracking.py:12-34) with everything device-resident: descriptors ``uint8[n,32]`` and
+    keypoint coordinates ``float32[n,2]`` are CUDA tensors; the search, the ratio loop (with its truncation at the
+    first short row), the compaction of ``good`` and both gathers run on the GPU.  Returns ``(q1, q2)`` CUDA
+    tensors ``float32[M,2]``."""
+    import torch
+    for xy in (kp1_xy, kp2_xy):
+        if xy.dtype != torch.float32 or xy.dim() != 2:
+            raise ValueError("keypoint coordinates must be float32[n, k] CUDA tensors")
+    idx, dist, acc = knn2(des1, des2, ratio=ratio)
+    q1, q2 = _compact_and_gather(idx, dist, acc, [(0, kp1_xy), (1, kp2_xy)])
+    return q1, q2
+
+
+def find_2d_3d_device(des_i, kp_i_xy, kp_i1_xy, des_i1, pts3d, max_distance=1000, ratio=REFERENCE_RATIO):
+    """Point3D.find_2D_and_3D_correspondenses (Point3D.py:33-54) device-resident: kNN-2 + ratio 0.7, then a match is kept
+    only if the query's triangulated point has |X|, |Y|, |Z| < max_Distance (Point3D.py:45-46; slm_filter_points3d), then
+    the three gathers of Point3D.py:50-52.  ``pts3d`` is ``float64[nq,3]``.  Returns ``(q2, Q1, q1)`` like the reference:
+    train keypoints of the kept matches, their 3-D points, their query keypoints."""
+    import torch
+    if pts3d.dtype != torch.float64 or pts3d.dim() != 2 or pts3d.shape[1] != 3:
+        raise ValueError("pts3d must be a float64[nq, 3] CUDA tensor")
+    idx, dist, acc = knn2(des_i, des_i1, ratio=ratio)
+    dev, nq = idx.device, idx.shape[0]
+    if pts3d.shape[0] != nq:
+        raise ValueError("one 3-D point per query descriptor")
+    if nq:
+        ctx = _lib.context(dev.index or 0)
+        p = pts3d.contiguous()
+        _lib.check(ctx.lib.slm_filter_points3d(ctx.handle, p.data_ptr(), nq, float(max_distance), acc.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream))
+    q2, Q1, q1 = _compact_and_gather(idx, dist, acc, [(1, kp_i1_xy), (0, pts3d), (0, kp_i_xy)])
+    return q2, Q1, q1
+
+
+def stereo_matches_device(kp_left_xy, des_left, kp_right_xy, des_right, ratio=REFERENCE_RATIO):
+    """keypoint.track_keypoints_left_to_right_new (keypoint.py:35-57) up to its fundamental-matrix step, device-resident:
+    kNN-2 + ratio 0.7 and the four gathers -- left / right keypoint coordinates and left / right DESCRIPTORS of the good
+    matches (keypoint.py:53-57).  Returns ``(pts_left, pts_right, des_left_good, des_right_good)`` CUDA tensors."""
+    idx, dist, acc = knn2(des_left, des_right, ratio=ratio)
+    dl = _dev_desc(des_left, "descriptors_left")
+    dr = _dev_desc(des_right, "descriptors_right")
+    return tuple(_compact_and_gather(idx, dist, acc, [(0, kp_left_xy), (1, kp_right_xy), (0, dl), (1, dr)]))

@@ -167,7 +167,62 @@ def gen_reference_functions():
     print("reference_functions.npz:", len(out["names"]), "cases")
 
 
+def gen_reference_stereo():
+    """keypoint.track_keypoints_left_to_right_new (keypoint.py:35-78) run UNMODIFIED up to its fundamental-matrix step:
+    cv2.findFundamentalMat is intercepted, the four gathered arrays of keypoint.py:53-57 (pts_left, pts_right, des_left,
+    des_right) are read from the reference function's own frame, and the call is aborted there (what follows is RANSAC-like
+    sampling and cv2.imshow, which the headless OpenCV build does not have)."""
+    sys.path.insert(0, REFERENCE)
+    import keypoint  # /root/reference/keypoint.py
+
+    class _Captured(Exception):
+        pass
+
+    grabbed = {}
+
+    def fake_fundamental(pts_left, pts_right, method=None, *a, **k):
+        loc = sys._getframe(1).f_locals
+        for name in ("pts_left", "pts_right", "des_left", "des_right"):
+            grabbed[name] = np.array(loc[name])
+        raise _Captured()
+
+    flann_ctor, fmat = cv2.FlannBasedMatcher, cv2.findFundamentalMat
+    cv2.FlannBasedMatcher = lambda indexParams=None, searchParams=None: cv2.BFMatcher(cv2.NORM_HAMMING)
+    cv2.findFundamentalMat = fake_fundamental
+    out, names = {}, []
+    try:
+        for kind, nq, nt, seed in [("planted", 700, 800, 31), ("planted", 1000, 1000, 32), ("ties", 90, 200, 33),
+                                   ("planted", 40, 1, 34)]:
+            q, t = make_inputs(kind, nq, nt, seed)
+            rng = np.random.default_rng(seed + 7)
+            p1 = rng.uniform(0, 1226, size=(nq, 2)).astype(np.float32)
+            p2 = rng.uniform(0, 370, size=(nt, 2)).astype(np.float32)
+            kp1 = [cv2.KeyPoint(float(x), float(y), 31.0) for x, y in p1]
+            kp2 = [cv2.KeyPoint(float(x), float(y), 31.0) for x, y in p2]
+            grabbed.clear()
+            try:
+                keypoint.track_keypoints_left_to_right_new(kp1, q, kp2, t, None, None)
+            except _Captured:
+                pass
+            name = f"{kind}_{nq}x{nt}_s{seed}"
+            names.append(name)
+            out[name + "/q"], out[name + "/t"], out[name + "/p1"], out[name + "/p2"] = q, t, p1, p2
+            out[name + "/pts_left"] = np.asarray(grabbed["pts_left"], dtype=np.float64).reshape(-1, 2)
+            out[name + "/pts_right"] = np.asarray(grabbed["pts_right"], dtype=np.float64).reshape(-1, 2)
+            out[name + "/des_left"] = np.asarray(grabbed["des_left"], dtype=np.uint8).reshape(-1, 32)
+            out[name + "/des_right"] = np.asarray(grabbed["des_right"], dtype=np.uint8).reshape(-1, 32)
+        out["names"] = np.array(names)
+    finally:
+        cv2.FlannBasedMatcher, cv2.findFundamentalMat = flann_ctor, fmat
+    np.savez_compressed(os.path.join(HERE, "reference_stereo.npz"), **out)
+    print("reference_stereo.npz:", len(names), "cases", [out[n + "/pts_left"].shape[0] for n in names])
+
+
 if __name__ == "__main__":
-    gen_knn2()
-    gen_ratio_table()
-    gen_reference_functions()
+    if len(sys.argv) > 1 and sys.argv[1] == "stereo":
+        gen_reference_stereo()
+    else:
+        gen_knn2()
+        gen_ratio_table()
+        gen_reference_functions()
+        gen_reference_stereo()

@@ -50,10 +50,39 @@ class _Ranks:
         for c in self.ctxs:
             c.close()
 
+    def _warm(self, q_dev, shards, bounds, variant, fused):
+        """Load every kernel the concurrent step will launch, one rank at a time.  CUDA loads kernels lazily at their first
+        launch and a load may wait for running kernels to finish -- on ONE GPU that would deadlock against another
+        'rank' whose merge kernel is polling for this rank's flags.  (No issue across real GPUs: one process per device.)"""
+        import torch
+        nq = q_dev.shape[0]
+        keys = torch.zeros((2, 1, self.cap, 2), dtype=torch.int64, device="cuda")
+        flags = torch.zeros((2,), dtype=torch.int32, device="cuda")
+        kp, fp = (ctypes.c_uint64 * 1)(keys.data_ptr()), (ctypes.c_uint64 * 1)(flags.data_ptr())
+        idx = torch.empty((nq, 2), dtype=torch.int32, device="cuda")
+        ctx = self.ctxs[0]
+        for r in range(self.world):
+            t, (a, b) = shards[r], bounds[r]
+            with ctx.using(variant):
+                if fused:
+                    _lib.check(ctx.lib.slm_knn2_exchange(ctx.handle, q_dev.data_ptr(), nq, t.data_ptr() if b > a else None, b - a,
+                                                         a, self.cap, 0, ctypes.cast(kp, ctypes.c_void_p),
+                                                         ctypes.cast(fp, ctypes.c_void_p), 0, 1, r + 1, 7, 10, idx.data_ptr(),
+                                                         None, None, None))
+                else:
+                    k = torch.empty((nq, 2), dtype=torch.int64, device="cuda")
+                    _lib.check(ctx.lib.slm_knn2_keys(ctx.handle, q_dev.data_ptr(), nq, t.data_ptr() if b > a else None, b - a, a,
+                                                     k.data_ptr(), None))
+                    _lib.check(ctx.lib.slm_exchange_merge(ctx.handle, k.data_ptr(), nq, self.cap, 0, ctypes.cast(kp, ctypes.c_void_p),
+                                                          ctypes.cast(fp, ctypes.c_void_p), 0, 1, r + 1, 7, 10, idx.data_ptr(),
+                                                          None, None, None))
+            torch.cuda.synchronize()
+
     def query(self, q_dev, shards, bounds, total_rows, ratio, variant, fused=True):
         """One sharded step on all ranks; returns every rank's (idx, dist, acc) as numpy."""
         import torch
         nq = q_dev.shape[0]
+        self._warm(q_dev, shards, bounds, variant, fused)
         self.step += 1
         outs = []
         for r in range(self.world):
