@@ -23,6 +23,7 @@
 // (tc_params.cuh); the exact top-2 rows lie inside the best two chunks, which tc_refine_kernel re-scores with XOR+POPC.
 #include <atomic>
 #include <cfloat>
+#include <type_traits>
 
 #include "slm_internal.cuh"
 #include "exchange.cuh"
@@ -86,6 +87,28 @@ __device__ __forceinline__ void iter_next(TileIter &it, const TcParams &p, int t
     }
 }
 
+// tcgen05.wait::ld that cannot be scheduled before `x` has been computed.  ptxas freely sinks the FMNMX reduction of piece
+// k below the (operand-less) wait for piece k + 1, which exposes the TMEM read latency again (first ncu source view of
+// this kernel: all stall samples sat on the wait right behind the LDTM).  Predicating the wait on the reduction's result
+// -- always true: every dot product is >= -256 -- makes the order a data dependency.
+__device__ __forceinline__ void tmem_wait_ld_after(float x)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.gt.f32 p, %0, 0fF149F2CA;\n\t"          // x > -1e30
+                 "@p tcgen05.wait::ld.sync.aligned;\n\t}" ::"f"(x) : "memory");
+}
+
+// mbarrier wait of the hot loop: no spin counter, no printf path (the bounded tc::mbar_wait costs ~10 extra instructions and
+// a call frame per job).  Every barrier of this kernel is also waited for by a bounded wait somewhere (expanders, MMA
+// issuer), so a protocol bug still ends in their trap rather than in a hang.
+__device__ __forceinline__ void mbar_wait_lean(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra WAIT_%=;\n\t}" ::"r"(tc::smem_u32(bar)), "r"(parity) : "memory");
+}
+
 template <int C>
 __device__ __forceinline__ float max_cols(const uint32_t *v)
 {
@@ -117,7 +140,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
     Bars4 *bars = reinterpret_cast<Bars4 *>(sRaw + kRawStages * kRawBytes);
 
     slm_pdl_launch_dependents();       // the refine kernel may start launching; it waits for this grid's results
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);   // warp-uniform for the compiler: TMEM addresses live in uniform registers
     const uint32_t rank = tc::cluster_ctarank();          // 0 = leader
     const int item = blockIdx.x >> 1;                     // cluster index
     const int gpair = item / p.cpg;                       // pair of query groups served by this cluster
@@ -202,68 +226,83 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
             t2 = fmaxf(t2, fminf(t1, key));
             t1 = fmaxf(t1, key);
         };
+        // Jobs per train tile, padded to an even count: the accumulator (job & 1) and the register buffers of the software
+        // pipeline then depend on the compile-time m only.  (The padding job of an odd count repeats the last query tile;
+        // nobody tracks its result.)
+        const int mt_jobs = (mt_pair + 1) & ~1;
         int job = 0, epoch = 0, lt = 0, j = 0, last_r = -1;     // lt = tiles seen in this epoch, j = ranges walked
+        uint32_t X[40], Y[40], Z[40];        // three 40-column register buffers
+        auto valid_cols_of = [&](const TileIter &ti) { return min(tc4::kTileN, p.nt - (ti.r * p.range_tiles + ti.bt) * tc4::kTileN); };
         TileIter it;
         for (iter_start(it, p, unit, total_tiles); !it.done; iter_next(it, p, total_tiles), ++lt) {
             if (it.r != last_r) {
                 if (last_r >= 0 && ++j % p.rpe == 0) { flush(epoch); ++epoch; lt = 0; }
                 last_r = it.r;
             }
-            const int tile = it.r * p.range_tiles + it.bt;
-            const int valid_cols = min(tc4::kTileN, p.nt - tile * tc4::kTileN);
+            const int valid_cols = valid_cols_of(it);
+            const int col0 = set * kHalf;
+            const bool tile_active = col0 < valid_cols;
             // chunk k of this set covers columns [set * 120 + k * CH, + CH); counter of the first one
             const float bias0 = (float)(kChunkMask - (lt * kCPT + set * kCPS));
-            const int col0 = set * kHalf;
-#pragma unroll
-            for (int m = 0; m < kMaxMT4; ++m) {
-                if (m < mt_pair) {
-                    const int ab = job & 1;
-                    tc::mbar_wait(&bars->acc_full[ab], (job >> 1) & 1, 10 + ab);
-                    tc::tc_fence_after();
-                    if (m < mt_mine && col0 < valid_cols) {
-                        const uint32_t acc = lane_addr + ab * tc4::kTileN;
-                        // all loads of this warp's 120 columns in flight at once; the accumulator is handed back as soon
-                        // as they have landed, BEFORE the reduction
-                        uint32_t v0[64], v1[32], v2[16], v3[8];
-                        if constexpr (CH == 120) {
-                            tc::tmem_ldx64(acc, v0);
-                            tc::tmem_ldx32(acc + 64, v1);
-                            tc::tmem_ldx16(acc + 96, v2);
-                            tc::tmem_ldx8(acc + 112, v3);
-                        } else {
-                            // three chunks of 40 = 32 + 8 columns: v1 | v3, v0[0..32) | v2[0..8), v0[32..64) | v2[8..16)
-                            tc::tmem_ldx32(acc, v1);
-                            tc::tmem_ldx8(acc + 32, v3);
-                            tc::tmem_ldx32(acc + 40, v0);
-                            tc::tmem_ldx8(acc + 72, v2);
-                            tc::tmem_ldx32(acc + 80, v0 + 32);
-                            tc::tmem_ldx8(acc + 112, v2 + 8);
-                        }
+            auto one_job = [&](auto m_const) {
+                constexpr int m = decltype(m_const)::value;
+                if (m < mt_jobs) {
+                    constexpr int ab = m & 1;
+                    const uint32_t ph = (uint32_t)(job >> 1) & 1u;
+                    const uint32_t acc = lane_addr + ab * tc4::kTileN;
+                    const bool active = tile_active && m < mt_mine;
+                    if (active) {
+                        // Three 40-column pieces: pieces 0 and 1 are requested together, piece 2 as soon as they have landed;
+                        // the accumulator is handed back when piece 2 has landed, i.e. after ONE reduction (piece 0), and the
+                        // TMEM read of piece 2 (128 x 240 x 4 B per job = 131 clk of TMEM bandwidth per SM) overlaps that
+                        // reduction.  Hand-back latency is what the MMA waits for with only two accumulators.
+                        mbar_wait_lean(&bars->acc_full[ab], ph);
+                        tc::tc_fence_after();
+                        tc::tmem_ldx32(acc, X);
+                        tc::tmem_ldx8(acc + 32, X + 32);
+                        tc::tmem_ldx32(acc + 40, Y);
+                        tc::tmem_ldx8(acc + 72, Y + 32);
                         tc::tmem_wait_ld();
-                        tc::tmem_pin64(v0);
-                        tc::tmem_pin32(v1);
-                        tc::tmem_pin16(v2);
-                        tc::tmem_pin8(v3);
+                        tc::tmem_pin32(X);
+                        tc::tmem_pin8(X + 32);
+                        tc::tmem_pin32(Y);
+                        tc::tmem_pin8(Y + 32);
+                        tc::tmem_ldx32(acc + 80, Z);
+                        tc::tmem_ldx8(acc + 112, Z + 32);
+                        const float mx0 = fmaxf(max_cols<32>(X), max_cols<8>(X + 32));
+                        tmem_wait_ld_after(mx0);  // piece 0 is reduced while piece 2 is in flight
+                        tc::tmem_pin32(Z);
+                        tc::tmem_pin8(Z + 32);
                         tc::tc_fence_before();
                         tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
+                        const float mx1 = fmaxf(max_cols<32>(Y), max_cols<8>(Y + 32));
+                        const float mx2 = fmaxf(max_cols<32>(Z), max_cols<8>(Z + 32));
                         if constexpr (CH == 120) {
-                            const float mx = fmaxf(fmaxf(max_cols<64>(v0), max_cols<32>(v1)), fmaxf(max_cols<16>(v2), max_cols<8>(v3)));
-                            track(b1[m], b2[m], fmaf(mx, kKeyScale, bias0));
+                            track(b1[m], b2[m], fmaf(fmaxf(fmaxf(mx0, mx1), mx2), kKeyScale, bias0));
                         } else {
-                            const float mx0 = fmaxf(max_cols<32>(v1), max_cols<8>(v3));
-                            const float mx1 = fmaxf(max_cols<32>(v0), max_cols<8>(v2));
-                            const float mx2 = fmaxf(max_cols<32>(v0 + 32), max_cols<8>(v2 + 8));
                             track(b1[m], b2[m], fmaf(mx0, kKeyScale, bias0));
                             if (col0 + 40 < valid_cols) track(b1[m], b2[m], fmaf(mx1, kKeyScale, bias0 - 1.0f));
                             if (col0 + 80 < valid_cols) track(b1[m], b2[m], fmaf(mx2, kKeyScale, bias0 - 2.0f));
                         }
                     } else {
+                        // nothing to read for this warp (idle half of a pair, padding job, columns past the train set)
+                        mbar_wait_lean(&bars->acc_full[ab], ph);
+                        tc::tc_fence_after();
                         tc::tc_fence_before();
                         tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
                     }
                     ++job;
                 }
-            }
+            };
+            one_job(std::integral_constant<int, 0>{});
+            one_job(std::integral_constant<int, 1>{});
+            one_job(std::integral_constant<int, 2>{});
+            one_job(std::integral_constant<int, 3>{});
+            one_job(std::integral_constant<int, 4>{});
+            one_job(std::integral_constant<int, 5>{});
+            one_job(std::integral_constant<int, 6>{});
+            one_job(std::integral_constant<int, 7>{});
+            static_assert(kMaxMT4 == 8, "one_job is instantiated for m = 0..7");
         }
         for (; epoch < p.n_epochs; ++epoch) flush(epoch);     // remaining epochs are written as "none"
     } else if (warp < mma_warp) {
@@ -330,18 +369,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
             const uint32_t sf = tmem + tc4::kSfCol;
             tc::mbar_wait_cluster(&bars->a_full, 0, 30);
             tc::tc_fence_after();
+            const int mt_jobs = (mt_pair + 1) & ~1;
             int job = 0, s = 0, ph = 0;
             TileIter it;
             for (iter_start(it, p, unit, total_tiles); !it.done; iter_next(it, p, total_tiles)) {
                 tc::mbar_wait_cluster(&bars->b_full[s], ph, 31 + s);
                 tc::tc_fence_after();
                 const uint32_t b_lo = b_lo0 + s * (tc4::kBHalfBytes >> 4);
-                for (int m = 0; m < mt_pair; ++m) {
+                for (int m = 0; m < mt_jobs; ++m) {          // even: the padding job repeats the last query tile
                     const int ab = job & 1;
                     tc::mbar_wait_cluster(&bars->acc_empty[ab], ((job >> 1) & 1) ^ 1, 40 + ab);
                     tc::tc_fence_after();
                     if (tc::elect_one()) {
-                        tc4::umma_job(tmem + ab * tc4::kTileN, a_lo0 + m * (tc4::kATileBytes >> 4), b_lo, idesc, sf);
+                        tc4::umma_job(tmem + ab * tc4::kTileN, a_lo0 + min(m, mt_pair - 1) * (tc4::kATileBytes >> 4), b_lo, idesc, sf);
                         tc::umma_commit_2cta(&bars->acc_full[ab], 3);
                     }
                     __syncwarp();

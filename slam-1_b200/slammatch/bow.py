@@ -124,8 +124,13 @@ class BoW:
         return self._db[: self._n].cpu().numpy().astype(np.int64)
 
     # -- bag_of_words.py:29-53 ------------------------------------------------------------------------
+    MAX_SCAN_WORDS = 12288     # slm_chi2_scan stages the query histogram in 48 KB of shared memory (include/slammatch.h)
+
     def _scan(self, hist_dev, n_db: int):
         import torch
+        if self.n_clusters > self.MAX_SCAN_WORDS:
+            raise ValueError(f"predict / predict_previous support vocabularies of at most {self.MAX_SCAN_WORDS} words "
+                             f"(this one has {self.n_clusters}); hist() and word assignment have no such limit")
         dist = torch.empty(n_db, dtype=torch.float64, device=self.device)
         best_i = torch.empty(1, dtype=torch.int32, device=self.device)
         best_v = torch.empty(1, dtype=torch.float64, device=self.device)

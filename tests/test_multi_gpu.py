@@ -1,5 +1,7 @@
-"""Sharded train set over >= 2 real GPUs with NCCL (skipped on a single-GPU box): every rank must return the
-oracle's result bit-exactly, i.e. the same bytes as the 1-GPU path, for 2..N shards."""
+"""Sharded train set over >= 2 real GPUs with NCCL (skipped on a single-GPU box; the single-GPU loopback of the same
+kernels is tests/test_exchange_loopback_gpu.py): every rank must return the oracle's result bit-exactly, i.e. the same
+bytes as the 1-GPU path, for 2..N shards, every exchange (NCCL all-gather, NVLink peer stores, all-to-all), both key
+widths, and query batches above the old 8192-query limit of the NVLink exchange."""
 import os
 import socket
 
@@ -7,6 +9,10 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+# (name, nq, nt, seed): config-5-like (few queries, long DB, 64-bit keys) and config-4-like (many queries, <= 65536 words,
+# 32-bit keys on the NVLink exchange)
+CASES = [("c5like", 512, 300_000, 17), ("c4like", 20_000, 60_000, 19)]
 
 
 def _free_port():
@@ -17,25 +23,41 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, q, t, out_dir, exchange="auto"):
+def _worker(rank, world, port, out_dir, exchange):
     import torch
     import torch.distributed as dist
+    import slammatch
+    from slammatch import synth
     from slammatch.sharded import ShardedMatcher, shard_bounds
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        a, b = shard_bounds(t.shape[0], world)[rank]
-        sm = ShardedMatcher(torch.from_numpy(t[a:b]).cuda(), a, ratio=(7, 10), exchange=exchange)
-        qd = torch.from_numpy(q).cuda()
-        for _ in range(5):                    # several steps: both halves of the exchange buffers get reused
-            idx, dd, acc = sm.knn2(qd)
+        used = {}
+        for name, nq, nt, seed in CASES:
+            q, t = synth.planted(nq, nt, seed)
+            t = synth.with_duplicates(t, seed + 1, 0.2)
+            a, b = shard_bounds(nt, world)[rank]
+            sm = ShardedMatcher(torch.from_numpy(t[a:b]).cuda(), a, ratio=(7, 10), exchange=exchange)
+            qd = torch.from_numpy(q).cuda()
+            for _ in range(5):                    # several steps: both halves of the exchange buffers get reused
+                idx, dd, acc = sm.knn2(qd)
+            torch.cuda.synchronize()
+            sm.check()
+            used[name] = sm.last_exchange
+            np.savez(os.path.join(out_dir, f"{name}_rank{rank}.npz"), idx=idx.cpu().numpy(), dist=dd.cpu().numpy(),
+                     acc=acc.cpu().numpy())
+        # the sharded keyframe DB (round-robin keyframes, rebased keys) on the same ranks
+        frames = [synth.uniform(n, 4000 + i) for i, n in enumerate((700, 3, 1200, 0, 64, 900, 333))]
+        db = slammatch.ShardedKeyframeDB(device=rank, capacity=256)
+        for f in frames:
+            db.add(f)
+        qk = np.concatenate(frames)[::7][:300] ^ np.uint8(2)
+        i, d, a = db.query(qk)
+        np.savez(os.path.join(out_dir, f"kfdb_rank{rank}.npz"), idx=i, dist=d, acc=a)
         if rank == 0:
-            open(os.path.join(out_dir, "exchange.txt"), "w").write(sm.last_exchange)
-        torch.cuda.synchronize()
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx.cpu().numpy(), dist=dd.cpu().numpy(),
-                 acc=acc.cpu().numpy())
+            open(os.path.join(out_dir, "exchange.txt"), "w").write(repr(used))
     finally:
         dist.destroy_process_group()
 
@@ -48,14 +70,22 @@ def test_nccl_sharded_query_equals_oracle(tmp_path):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    q, t = synth.planted(512, 300_000, 17)
-    t = synth.with_duplicates(t, 18, 0.2)
-    oi, od = orc.c_knn2(q, t)
+    want = {}
+    for name, nq, nt, seed in CASES:
+        q, t = synth.planted(nq, nt, seed)
+        t = synth.with_duplicates(t, seed + 1, 0.2)
+        want[name] = orc.c_knn2(q, t)
+    frames = [synth.uniform(m, 4000 + i) for i, m in enumerate((700, 3, 1200, 0, 64, 900, 333))]
+    flat = np.concatenate(frames)
+    qk = flat[::7][:300] ^ np.uint8(2)
+    want["kfdb"] = orc.c_knn2(qk, flat)
     for world in sorted({2, n}):
         for exchange in ("nccl", "auto", "a2a"):
-            mp.spawn(_worker, args=(world, _free_port(), q, t, str(tmp_path), exchange), nprocs=world, join=True)
+            mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), exchange), nprocs=world, join=True)
             print("world", world, "exchange requested", exchange, "used", open(tmp_path / "exchange.txt").read())
             for r in range(world):
-                z = np.load(tmp_path / f"rank{r}.npz")
-                assert np.array_equal(z["idx"], oi) and np.array_equal(z["dist"], od), (world, r, exchange)
-                assert np.array_equal(z["acc"], orc.c_ratio(od, 7, 10)), (world, r, exchange)
+                for name in list(x[0] for x in CASES) + ["kfdb"]:
+                    z = np.load(tmp_path / f"{name}_rank{r}.npz")
+                    oi, od = want[name]
+                    assert np.array_equal(z["idx"], oi) and np.array_equal(z["dist"], od), (world, r, exchange, name)
+                    assert np.array_equal(z["acc"], orc.c_ratio(od, 7, 10)), (world, r, exchange, name)
