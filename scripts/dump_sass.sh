@@ -18,3 +18,9 @@ dump "tc_refine_frame_kernel" r1_tc_refine_frame_kernel.sass
 dump "knn2_frame_kernelILi2ELi8" r1_knn2_frame_kernel_kq2_w8.sass
 dump "vocab_majority_kernel" r1_vocab_majority_kernel.sass
 grep -c "UTCQMMA" profiles/sass/r1_knn2_tc2_kernel_mt4.sass
+# round 2
+dump "knn2_tc4_kernelILi120" r2_knn2_tc4_kernel_ch120.sass
+dump "knn2_tc4_kernelILi40" r2_knn2_tc4_kernel_ch40.sass
+dump "exchange_wait_merge_kernel" r2_exchange_wait_merge_kernel.sass
+dump "tc_refine_kernelILi32" r2_tc_refine_kernel_g32.sass
+echo "UTCOMMA $(grep -c UTCOMMA profiles/sass/r2_knn2_tc4_kernel_ch120.sass)  UBLKCP $(grep -c UBLKCP profiles/sass/r2_knn2_tc4_kernel_ch120.sass)  LDTM $(grep -c LDTM profiles/sass/r2_knn2_tc4_kernel_ch120.sass)  LDL $(grep -c 'LDL' profiles/sass/r2_knn2_tc4_kernel_ch120.sass)"

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) exchange_store_kernel(slm_exchange ex, co
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq) {
         const ulonglong2 k = reinterpret_cast<const ulonglong2 *>(local_keys)[i];
-        slm_exchange_store(ex, i, k.x, k.y);
+        for (int r = 0; r < ex.world; ++r) slm_exchange_store_to(ex, r, i, k.x, k.y);     // consecutive threads, consecutive queries
     }
     slm_exchange_publish(ex);
 }

@@ -22,26 +22,23 @@ __device__ __forceinline__ unsigned long long slm_key_widen(unsigned k)
     return k == 0xFFFFFFFFu ? kKeyNone : ((unsigned long long)(k >> 16) << 32) | (unsigned long long)(k & 0xFFFFu);
 }
 
-// Store query q's keys into slot [step & 1][rank][q] of every rank's buffer.
-__device__ __forceinline__ void slm_exchange_store(const slm_exchange &ex, long long q, unsigned long long k1,
-                                                   unsigned long long k2)
+// Store query q's keys into slot [step & 1][rank][q] of ONE rank's buffer (callers spread (peer, query) pairs over threads
+// so that consecutive threads write consecutive queries of the same peer).
+__device__ __forceinline__ void slm_exchange_store_to(const slm_exchange &ex, int peer, long long q, unsigned long long k1,
+                                                      unsigned long long k2)
 {
     const long long slot = ((long long)(ex.step & 1u) * ex.world + ex.rank) * ex.cap + q;
-    if (ex.key_bytes == 4) {
-        const uint2 kk = make_uint2(slm_key_compact(k1), slm_key_compact(k2));
-        for (int r = 0; r < ex.world; ++r) reinterpret_cast<uint2 *>(ex.peer_keys[r])[slot] = kk;
-    } else {
-        const ulonglong2 kk = make_ulonglong2(k1, k2);
-        for (int r = 0; r < ex.world; ++r) reinterpret_cast<ulonglong2 *>(ex.peer_keys[r])[slot] = kk;
-    }
+    if (ex.key_bytes == 4) reinterpret_cast<uint2 *>(ex.peer_keys[peer])[slot] = make_uint2(slm_key_compact(k1), slm_key_compact(k2));
+    else reinterpret_cast<ulonglong2 *>(ex.peer_keys[peer])[slot] = make_ulonglong2(k1, k2);
 }
 
 // Called by ALL threads of EVERY block of the producer kernel after their stores: the block that finishes last
 // publishes `step` into this rank's flag on every peer.
-__device__ __forceinline__ void slm_exchange_publish(const slm_exchange &ex)
+// `wrote` = this thread issued peer stores (only those threads need the system-scope fence).
+__device__ __forceinline__ void slm_exchange_publish(const slm_exchange &ex, bool wrote = true)
 {
     __shared__ bool s_last;
-    __threadfence_system();
+    if (wrote) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         s_last = atomicAdd(ex.done_counter, 1u) == gridDim.x - 1;

@@ -626,15 +626,24 @@ __device__ __forceinline__ unsigned long long refine_widen(unsigned k, unsigned 
 //   phase 2: re-score those 2 x chunk rows with XOR+POPC and keep the exact top-2 by (distance, global index).
 // Sharded path (ex.world > 0): the warp stores the query's keys straight into every peer's exchange buffer and the
 // kernel's last block publishes this rank's flags (exchange.cuh); exchange_wait_merge_kernel follows.
+constexpr int kRefineMaxIters = 8;
 template <int G>
 __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long base, unsigned long long *keys_out,
-                                                        slm_exchange ex)
+                                                        slm_exchange ex, int iters)
 {
     constexpr int kQPW = 32 / G;   // queries per warp
+    constexpr int kQPB = 8 * kQPW; // queries per block and iteration (256 threads)
+    // sharded path: the block's keys are staged here and leave as contiguous runs, one per peer
+    __shared__ ulonglong2 s_keys[kQPB * kRefineMaxIters];
     slm_pdl_launch_dependents();   // the exchange's wait + merge kernel may become resident while this one drains
     const int lane = threadIdx.x & 31, sub = lane % G;
-    const long long gq = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kQPW + lane / G;
-    const bool live = gq < (long long)p.n_prob * p.nq;
+    const long long n_q = (long long)p.n_prob * p.nq;
+    const long long q_block = (long long)blockIdx.x * kQPB * iters;           // first query of this block
+    // `iters` consecutive groups of kQPB queries per block (> 1 only on the sharded path with many queries, where one
+    // system-scope fence per block is then amortised over 8 x as many peer stores)
+    for (int it = 0; it < iters; ++it) {
+    const long long gq = q_block + (long long)it * kQPB + (threadIdx.x >> 5) * kQPW + lane / G;
+    const bool live = gq < n_q;
     const long long gqc = live ? gq : 0;
     const int prob = (int)(gqc / p.nq);
     const int qi = (int)(gqc % p.nq);
@@ -647,7 +656,7 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
     }
     const uint4 *qs = reinterpret_cast<const uint4 *>(q + (long long)qi * 8);
     const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);        // inputs of the call: readable before the search has finished
-    slm_pdl_wait();                                        // the candidate keys of the search kernel are visible from here
+    if (it == 0) slm_pdl_wait();                           // the candidate keys of the search kernel are visible from here
     // ---- phase 1 ----
     const int n_cand = p.cpg * p.n_epochs * 4;   // (unit, epoch, set, best/second)
     const float *cand = reinterpret_cast<const float *>(p.cand) + gqc * (long long)n_cand;
@@ -699,9 +708,22 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
     if (live && sub == 0) {
         const unsigned long long w1 = refine_widen(k1, glo, ghi, p.chunk, base), w2 = refine_widen(k2, glo, ghi, p.chunk, base);
         if (keys_out) reinterpret_cast<ulonglong2 *>(keys_out)[gq] = make_ulonglong2(w1, w2);
-        if (ex.world > 0) slm_exchange_store(ex, gq, w1, w2);
+        if (ex.world > 0) s_keys[it * kQPB + (threadIdx.x >> 5) * kQPW + lane / G] = make_ulonglong2(w1, w2);
     }
-    if (ex.world > 0) slm_exchange_publish(ex);
+    }   // iterations
+    if (ex.world > 0) {
+        // a run of 32 queries is 256 B of compact keys: whole NVLink packets instead of scattered 8-byte stores; only the
+        // threads that stored fence (a system-scope fence per thread of every block was 0.2 ms on config 4)
+        __syncthreads();
+        const int n_here = (int)max(0ll, min((long long)kQPB * iters, n_q - q_block));
+        bool wrote = false;
+        for (int i = threadIdx.x; i < n_here * ex.world; i += blockDim.x) {
+            const int r = i / n_here, k = i - r * n_here;
+            slm_exchange_store_to(ex, r, q_block + k, s_keys[k].x, s_keys[k].y);
+            wrote = true;
+        }
+        slm_exchange_publish(ex, wrote);
+    }
 }
 
 // Refine for batches of frame-sized problems (config 3).  tc_refine_kernel reads every query's candidate rows
@@ -986,11 +1008,13 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         SLM_CUDA(slm_launch(tc_refine_frame_kernel, dim3((unsigned)n_prob), dim3(kRefineFrameThreads), frame_smem, stream, pdl, p,
                             reinterpret_cast<unsigned long long *>(keys_out)));
     } else if (p.cpg * p.n_epochs * 4 <= 32) {   // few candidates per query (many queries, short train sets): 8 lanes each
-        SLM_CUDA(slm_launch(tc_refine_kernel<8>, dim3((unsigned)((n_q + 31) / 32)), dim3(256), 0, stream, pdl, p, base,
-                            reinterpret_cast<unsigned long long *>(keys_out), ex));
+        // sharded path with many queries: 8 groups of 32 queries per block (one fence + one counter update per 256 queries)
+        const int iters = (exchange && n_q >= 65536) ? kRefineMaxIters : 1;
+        SLM_CUDA(slm_launch(tc_refine_kernel<8>, dim3((unsigned)((n_q + 32 * iters - 1) / (32 * iters))), dim3(256), 0, stream, pdl, p,
+                            base, reinterpret_cast<unsigned long long *>(keys_out), ex, iters));
     } else {                          // many ranges (long train sets): a full warp per query
         SLM_CUDA(slm_launch(tc_refine_kernel<32>, dim3((unsigned)((n_q + 7) / 8)), dim3(256), 0, stream, pdl, p, base,
-                            reinterpret_cast<unsigned long long *>(keys_out), ex));
+                            reinterpret_cast<unsigned long long *>(keys_out), ex, 1));
     }
     ctx->launches += 2;
     return SLM_OK;

@@ -143,14 +143,15 @@ def test_loopback_exchange_equals_oracle_64bit_keys(world, variant):
         ranks.close()
 
 
-@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("world,nq", [(2, 20_000), (8, 20_000), (2, 70_000)])
 @pytest.mark.parametrize("variant", ["auto", "tensor"])
-def test_loopback_exchange_config4_regime_32bit_keys(world, variant):
+def test_loopback_exchange_config4_regime_32bit_keys(world, nq, variant):
     """Config 4 in miniature: many queries (above the old 8192 cap), a vocabulary of at most 65 536 words sharded by rows
-    -> compact 32-bit keys (distance << 16 | word), merge kernel with a capped grid."""
+    -> compact 32-bit keys (distance << 16 | word), merge kernel with a capped grid.  70 000 queries reach the refine
+    kernel's multi-group blocks (8 x 32 queries per block, one fence per block) that config 4 itself runs with."""
     import torch
-    nq, nt = 20_000, 48_000
-    ranks = _Ranks(world, cap=32768)
+    nt = 48_000 if nq <= 20_000 else 30_000
+    ranks = _Ranks(world, cap=1 << (nq - 1).bit_length())
     try:
         for step in range(3):
             q, t = _case(nq, nt, 1900 + 10 * step)
