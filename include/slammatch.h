@@ -145,10 +145,11 @@ int slm_merge_top2(slm_ctx *ctx, const uint64_t *gathered_keys_dev, int32_t n_sh
 /*
  * NVLink exchange + merge (the sharded path's replacement for all-gather + slm_merge_top2 when the gather buffers are
  * peer-mapped, e.g. torch symmetric memory over NVLink / NVSwitch).
- *   peer_keys_host[r]  : device address, valid on THIS GPU, of rank r's key buffer: 2 * world * nq_capacity * 16 bytes
- *                        (layout [2][world][nq_capacity][2] keys; 64-bit keys, or 32-bit compact keys
- *                        (distance << 16 | index) in the front half when nt_global <= 65536 -- config 4's vocabulary)
- *   peer_flags_host[r] : device address of rank r's flag array uint32[2][world] (zero-initialised once)
+ *   peer_keys_host[r]  : device address, valid on THIS GPU, of rank r's key buffer: 4 * world * nq_capacity * 16 bytes
+ *                        (layout [2 phases][2 halves][world][nq_capacity][2] keys; 64-bit keys, or 32-bit compact keys
+ *                        (distance << 16 | index) in the front half of every slot when nt_global <= 65536 -- config 4's
+ *                        vocabulary)
+ *   peer_flags_host[r] : device address of rank r's flag array uint32[2 phases][2 halves][world] (zero-initialised once)
  *   nt_global          : number of train rows over ALL ranks (selects the key width; must be the same on every rank;
  *                        0 = unknown, 64-bit keys)
  * A producer kernel stores this rank's nq x 2 keys into slot [step & 1][rank] of every peer's buffer (16- / 8-byte
@@ -169,6 +170,9 @@ int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys_dev, int64_t nq,
  * The whole sharded step in one call: search this rank's train block, exchange over NVLink, merge, finalise.
  * Arguments as slm_knn2_keys + slm_exchange_merge.  With the tensor variants the refine kernel is the producer (every
  * query's exact keys go straight into the peers' buffers); other variants run the search followed by a store kernel.
+ * From 32 768 queries on (config 4) the tensor variants take a two-phase form: the ranks first exchange every query's best
+ * two candidate-chunk keys (phase 0), each rank picks the GLOBAL best two chunks and re-scores only those inside its own row
+ * block, and the exact keys travel in phase 1 -- the exact re-scoring is then shared by the ranks instead of repeated on each.
  */
 int slm_knn2_exchange(slm_ctx *ctx, const uint32_t *q_dev, int64_t nq, const uint32_t *t_dev, int64_t nt,
                       int64_t train_index_base, int64_t nq_capacity, int64_t nt_global, const uint64_t *peer_keys_host,

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_multi_gpu.py tests/test_exchange_loopback_gpu.py -q -m gpu > gpurun_out/pytest_multi2.txt 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_multi2.txt
-for ex in auto nccl a2a; do
+for ex in auto nccl; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 --workload c4 --configs none --exchange $ex > gpurun_out/c4_${ex}_n2.json 2> gpurun_out/c4_${ex}_n2.err
   python -c "
 import json

@@ -210,6 +210,7 @@ int slm_create(int device, slm_ctx **ctx_out)
         long long v = atoll(e);
         if (v >= 1) ctx->exchange_max_blocks = v;
     }
+    if (const char *e = getenv("SLM_EXCHANGE_TWO_PHASE_MIN")) ctx->exchange_two_phase_min = atoll(e);
     if (const char *e = getenv("SLM_EXCHANGE_MAX_POLLS")) {
         long long v = atoll(e);
         if (v >= 1 && v <= 0xFFFFFFFFll) ctx->exchange_max_polls = (unsigned)v;
@@ -512,7 +513,7 @@ int slm_exchange_merge(slm_ctx *ctx, const uint64_t *local_keys, int64_t nq, int
     slm_exchange ex;
     SLM_TRY(slm_exchange_setup(ctx, &ex, peer_keys_host, peer_flags_host, rank, world, step, nq_capacity, nt_global));
     SLM_TRY(slm_exchange_store(ctx, ex, local_keys, nq, stream));
-    SLM_TRY(slm_exchange_wait_merge(ctx, ex, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out, stream));
+    SLM_TRY(slm_exchange_wait_merge(ctx, ex, 0, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out, stream));
     return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
 }
 
@@ -534,17 +535,19 @@ int slm_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_
     SLM_TRY(slm_prof_mark(ctx, stream, SLM_TAG_CALL_BEGIN));
     slm_exchange ex;
     SLM_TRY(slm_exchange_setup(ctx, &ex, peer_keys_host, peer_flags_host, rank, world, step, nq_capacity, nt_global));
+    int phase = 0;
     if (tensor) {
-        // the refine kernel is the producer: every query's exact keys go straight into the peers' buffers
+        // the refine kernel is the producer: every query's exact keys go straight into the peers' buffers (phase 0), or --
+        // many queries -- the ranks first exchange candidate-chunk keys and only the owners refine (exact keys in phase 1)
         const bool fp4 = ctx->variant == SLM_VARIANT_TENSOR4 || (ctx->variant == SLM_VARIANT_AUTO && ctx->tc_fp4);
-        SLM_TRY(slm_tc_knn2_exchange(ctx, q, nq, t, nt, base, ex, stream, fp4));
+        SLM_TRY(slm_tc_knn2_exchange(ctx, q, nq, t, nt, base, ex, stream, fp4, &phase));
     } else {
         SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)nq * 16));
         uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
         SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys, stream));
         SLM_TRY(slm_exchange_store(ctx, ex, keys, nq, stream));
     }
-    SLM_TRY(slm_exchange_wait_merge(ctx, ex, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out, stream));
+    SLM_TRY(slm_exchange_wait_merge(ctx, ex, phase, nq, ratio_num, ratio_den, idx_out, dist_out, accept_out, stream));
     return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
 }
 

@@ -39,42 +39,16 @@ __device__ __forceinline__ void top2_insert32(unsigned &k1, unsigned &k2, unsign
     k2 = min(k2, m);
 }
 
-__global__ void __launch_bounds__(256) exchange_wait_merge_kernel(slm_exchange ex, long long nq, int ratio_num, int ratio_den,
-                                                                  int *idx_out, int *dist_out, unsigned char *accept_out,
-                                                                  unsigned max_polls, volatile int *status)
+__global__ void __launch_bounds__(256) exchange_wait_merge_kernel(slm_exchange ex, int phase, long long nq, int ratio_num,
+                                                                  int ratio_den, int *idx_out, int *dist_out,
+                                                                  unsigned char *accept_out)
 {
-    __shared__ int s_failed;
-    const unsigned parity = ex.step & 1u;
-    if (threadIdx.x == 0) s_failed = 0;
-    __syncthreads();
-    if ((int)threadIdx.x < ex.world) {
-        const unsigned *mine = ex.peer_flags[ex.rank] + parity * ex.world + threadIdx.x;
-        unsigned v, polls = 0;
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-            if ((int)(v - ex.step) >= 0) break;
-            if (++polls > max_polls) {
-                // report instead of trapping: (code, rank that did not deliver, step, last value seen)
-                if (atomicExch(&s_failed, 1) == 0 && blockIdx.x == 0) {
-                    status[1] = (int)threadIdx.x;
-                    status[2] = (int)ex.step;
-                    status[3] = (int)v;
-                    __threadfence_system();
-                    status[0] = 1;
-                }
-                s_failed = 1;
-                break;
-            }
-            __nanosleep(polls < 64 ? 20 : 500);
-        }
-    }
-    __syncthreads();
-    if (s_failed) return;                       // outputs are left untouched; the host raises SLM_ERR_TIMEOUT
+    if (!slm_exchange_wait_flags(ex, phase)) return;      // outputs are left untouched; the host raises SLM_ERR_TIMEOUT
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
         unsigned long long k1 = kKeyNone, k2 = kKeyNone;
         if (ex.key_bytes == 4) {
-            const uint2 *g = reinterpret_cast<const uint2 *>(ex.peer_keys[ex.rank]) + (long long)parity * ex.world * ex.cap;
+            const uint2 *g = reinterpret_cast<const uint2 *>(ex.peer_keys[ex.rank]) + slm_exchange_slot(ex, phase, 0);
             unsigned c1 = 0xFFFFFFFFu, c2 = 0xFFFFFFFFu;
             for (int r = 0; r < ex.world; ++r) {
                 const uint2 v = g[(long long)r * ex.cap + i];
@@ -84,7 +58,7 @@ __global__ void __launch_bounds__(256) exchange_wait_merge_kernel(slm_exchange e
             k1 = slm_key_widen(c1);
             k2 = slm_key_widen(c2);
         } else {
-            const ulonglong2 *g = reinterpret_cast<const ulonglong2 *>(ex.peer_keys[ex.rank]) + (long long)parity * ex.world * ex.cap;
+            const ulonglong2 *g = reinterpret_cast<const ulonglong2 *>(ex.peer_keys[ex.rank]) + slm_exchange_slot(ex, phase, 0);
             for (int r = 0; r < ex.world; ++r) {
                 const ulonglong2 v = g[(long long)r * ex.cap + i];
                 top2_insert(k1, k2, v.x);
@@ -123,6 +97,8 @@ int slm_exchange_setup(slm_ctx *ctx, slm_exchange *ex, const uint64_t *peer_keys
     // every global train index < 65 536 (config 4's vocabulary): 32-bit keys, half the NVLink bytes
     ex->key_bytes = (nt_global > 0 && nt_global <= 65536 && !ctx->exchange_wide_keys) ? 4 : 8;
     ex->done_counter = ctx->done_counter;
+    ex->max_polls = ctx->exchange_max_polls;
+    SLM_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&ex->status), ctx->exchange_status, 0));
     return SLM_OK;
 }
 
@@ -134,17 +110,14 @@ int slm_exchange_store(slm_ctx *ctx, const slm_exchange &ex, const uint64_t *loc
     return SLM_OK;
 }
 
-int slm_exchange_wait_merge(slm_ctx *ctx, const slm_exchange &ex, int64_t nq, int32_t ratio_num, int32_t ratio_den,
+int slm_exchange_wait_merge(slm_ctx *ctx, const slm_exchange &ex, int phase, int64_t nq, int32_t ratio_num, int32_t ratio_den,
                             int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream)
 {
     long long blocks = (nq + 255) / 256;
     if (blocks > ctx->exchange_max_blocks) blocks = ctx->exchange_max_blocks;
     if (blocks < 1) blocks = 1;
-    int *status_dev = nullptr;
-    SLM_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&status_dev), ctx->exchange_status, 0));
-    SLM_CUDA(slm_launch(exchange_wait_merge_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, /*pdl=*/!ctx->no_pdl, ex, (long long)nq,
-                        (int)ratio_num, (int)ratio_den, idx_out, dist_out, accept_out, ctx->exchange_max_polls,
-                        (volatile int *)status_dev));
+    SLM_CUDA(slm_launch(exchange_wait_merge_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, /*pdl=*/!ctx->no_pdl, ex, phase,
+                        (long long)nq, (int)ratio_num, (int)ratio_den, idx_out, dist_out, accept_out));
     ctx->launches += 1;
     return SLM_OK;
 }

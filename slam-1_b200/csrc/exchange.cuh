@@ -24,18 +24,72 @@ __device__ __forceinline__ unsigned long long slm_key_widen(unsigned k)
 
 // Store query q's keys into slot [step & 1][rank][q] of ONE rank's buffer (callers spread (peer, query) pairs over threads
 // so that consecutive threads write consecutive queries of the same peer).
-__device__ __forceinline__ void slm_exchange_store_to(const slm_exchange &ex, int peer, long long q, unsigned long long k1,
-                                                      unsigned long long k2)
+// first key slot of (phase, this step's half, source rank) in any rank's buffer
+__device__ __forceinline__ long long slm_exchange_slot(const slm_exchange &ex, int phase, int src_rank)
 {
-    const long long slot = ((long long)(ex.step & 1u) * ex.world + ex.rank) * ex.cap + q;
+    return ((long long)(phase * 2 + (int)(ex.step & 1u)) * ex.world + src_rank) * ex.cap;
+}
+__device__ __forceinline__ void slm_exchange_store_to(const slm_exchange &ex, int peer, long long q, unsigned long long k1,
+                                                      unsigned long long k2, int phase = 0)
+{
+    const long long slot = slm_exchange_slot(ex, phase, ex.rank) + q;
     if (ex.key_bytes == 4) reinterpret_cast<uint2 *>(ex.peer_keys[peer])[slot] = make_uint2(slm_key_compact(k1), slm_key_compact(k2));
     else reinterpret_cast<ulonglong2 *>(ex.peer_keys[peer])[slot] = make_ulonglong2(k1, k2);
+}
+
+// Candidate-chunk keys of the two-phase form: ((max dot + 257) << 32) | ~first global row of the chunk, 0 = none; a 64-bit
+// max prefers the larger dot, then the chunk with the lower rows.  Compact form (whole train set <= 65 536 rows):
+// (dot + 257) << 22 | (0x3FFFFF - first row).
+__device__ __forceinline__ unsigned slm_chunk_compact(unsigned long long k)
+{
+    return k == 0 ? 0u : ((unsigned)(k >> 32) << 22) | (0x3FFFFFu - (0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull)));
+}
+__device__ __forceinline__ unsigned long long slm_chunk_widen(unsigned k)
+{
+    return k == 0 ? 0ull : ((unsigned long long)(k >> 22) << 32) | (unsigned long long)(0xFFFFFFFFu - (0x3FFFFFu - (k & 0x3FFFFFu)));
+}
+__device__ __forceinline__ void slm_exchange_store_chunks_to(const slm_exchange &ex, int peer, long long q, unsigned long long c1,
+                                                             unsigned long long c2)
+{
+    const long long slot = slm_exchange_slot(ex, 0, ex.rank) + q;
+    if (ex.key_bytes == 4) reinterpret_cast<uint2 *>(ex.peer_keys[peer])[slot] = make_uint2(slm_chunk_compact(c1), slm_chunk_compact(c2));
+    else reinterpret_cast<ulonglong2 *>(ex.peer_keys[peer])[slot] = make_ulonglong2(c1, c2);
+}
+// Poll this rank's own flags of `phase` until every rank shows this step (threads 0..world-1 of the block poll; bounded).
+// Returns false -- after reporting (code, rank, step, value) once per grid -- if a peer never delivered.
+__device__ __forceinline__ bool slm_exchange_wait_flags(const slm_exchange &ex, int phase)
+{
+    __shared__ int s_failed;
+    if (threadIdx.x == 0) s_failed = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < ex.world) {
+        const unsigned *mine = ex.peer_flags[ex.rank] + (phase * 2 + (int)(ex.step & 1u)) * ex.world + threadIdx.x;
+        unsigned v, polls = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - ex.step) >= 0) break;
+            if (++polls > ex.max_polls) {
+                if (atomicExch(&s_failed, 1) == 0 && blockIdx.x == 0) {
+                    volatile int *status = ex.status;
+                    status[1] = (int)threadIdx.x;
+                    status[2] = (int)ex.step;
+                    status[3] = (int)v;
+                    __threadfence_system();
+                    status[0] = 1;
+                }
+                break;
+            }
+            __nanosleep(polls < 64 ? 20 : 500);
+        }
+    }
+    __syncthreads();
+    return s_failed == 0;
 }
 
 // Called by ALL threads of EVERY block of the producer kernel after their stores: the block that finishes last
 // publishes `step` into this rank's flag on every peer.
 // `wrote` = this thread issued peer stores (only those threads need the system-scope fence).
-__device__ __forceinline__ void slm_exchange_publish(const slm_exchange &ex, bool wrote = true)
+__device__ __forceinline__ void slm_exchange_publish(const slm_exchange &ex, bool wrote = true, int phase = 0)
 {
     __shared__ bool s_last;
     if (wrote) __threadfence_system();
@@ -47,7 +101,7 @@ __device__ __forceinline__ void slm_exchange_publish(const slm_exchange &ex, boo
     __syncthreads();
     if (s_last && (int)threadIdx.x < ex.world) {
         __threadfence_system();
-        unsigned *flag = ex.peer_flags[threadIdx.x] + (ex.step & 1u) * ex.world + ex.rank;
+        unsigned *flag = ex.peer_flags[threadIdx.x] + (phase * 2 + (int)(ex.step & 1u)) * ex.world + ex.rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(ex.step) : "memory");
     }
 }

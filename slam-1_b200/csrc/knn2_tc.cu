@@ -668,6 +668,7 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
     if (n_cand <= 8) {
         for (int ci = 0; ci < n_cand; ++ci) consider(ci);          // every lane of the group scans all: no shuffles
     } else {
+#pragma unroll 4
         for (int ci = sub; ci < n_cand; ci += G) consider(ci);
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
@@ -686,14 +687,27 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
     for (int s = 0; s < 2; ++s) {
         const unsigned g = s == 0 ? glo : ghi;
         if (g == 0xFFFFFFFFu) continue;
-        for (int pos = sub; pos < p.chunk; pos += G) {
-            const long long row = (long long)g * p.chunk + pos;
-            if (row < p.nt) {
+        // four rows per lane in flight: the candidate rows come from HBM / L2 and every trip of a rolled loop would expose
+        // the full load latency (this loop was most of the refine kernel's 10 us on config 5)
+        for (int pos0 = sub; pos0 < p.chunk; pos0 += 4 * G) {
+            uint4 ta[4], tb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int pos = pos0 + u * G;
+                const long long row = min((long long)g * p.chunk + pos, (long long)p.nt - 1);
                 const uint4 *ts = reinterpret_cast<const uint4 *>(t + row * 8);
-                const unsigned key = refine_key(hamming256(qa, qb, __ldg(ts), __ldg(ts + 1)), s, pos);
-                const unsigned m = max(k1, key);
-                k1 = min(k1, key);
-                k2 = min(k2, m);
+                ta[u] = __ldg(ts);
+                tb[u] = __ldg(ts + 1);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int pos = pos0 + u * G;
+                if (pos < p.chunk && (long long)g * p.chunk + pos < p.nt) {
+                    const unsigned key = refine_key(hamming256(qa, qb, ta[u], tb[u]), s, pos);
+                    const unsigned m = max(k1, key);
+                    k1 = min(k1, key);
+                    k2 = min(k2, m);
+                }
             }
         }
     }
@@ -724,6 +738,153 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
         }
         slm_exchange_publish(ex, wrote);
     }
+}
+
+// ---- two-phase form of the sharded refine (many queries) ----------------------------------------
+// tc_refine_kernel re-scores two chunks per query ON EVERY RANK: constant work per rank, however many ranks share the train
+// set -- on config 4 (1M queries) that is 0.34 ms next to 0.6 ms of search at 8 ranks.  But the chunk keys already hold the
+// exact best distance of every chunk, and the proof of the single-GPU refine holds for the union of all ranks' chunks: the
+// global top-2 rows lie in the GLOBAL best two chunks by (max dot desc, first row asc).  So:
+//   phase 0  tc_chunk_keys_kernel     every rank sends its best two chunk keys per query (dot, first global row) to all ranks
+//   phase 1  tc_refine_owned_kernel   every rank picks the global best two chunks per query from all ranks' keys and
+//                                     re-scores only those that lie in ITS row block (on average 2 / world per query),
+//                                     then sends its exact top-2 of them; exchange_wait_merge_kernel merges as before.
+template <int G>
+__global__ void __launch_bounds__(256) tc_chunk_keys_kernel(TcParams p, long long base, slm_exchange ex, int iters)
+{
+    constexpr int kQPW = 32 / G, kQPB = 8 * kQPW;
+    __shared__ ulonglong2 s_keys[kQPB * kRefineMaxIters];
+    slm_pdl_launch_dependents();
+    const int lane = threadIdx.x & 31, sub = lane % G;
+    const long long n_q = p.nq;
+    const long long q_block = (long long)blockIdx.x * kQPB * iters;
+    slm_pdl_wait();
+    const int n_cand = p.cpg * p.n_epochs * 4;
+    for (int it = 0; it < iters; ++it) {
+        const long long gq = q_block + (long long)it * kQPB + (threadIdx.x >> 5) * kQPW + lane / G;
+        const bool live = gq < n_q;
+        const float *cand = reinterpret_cast<const float *>(p.cand) + (live ? gq : 0) * (long long)n_cand;
+        unsigned long long c1 = 0, c2 = 0;
+        auto consider = [&](int ci) {
+            const float key = cand[ci];
+            if (key > -1.0e30f) top2_insert_max(c1, c2, cand_to_chunk_key(p, key, ci >> 2));
+        };
+        if (n_cand <= 8) {
+            for (int ci = 0; ci < n_cand; ++ci) consider(ci);
+        } else {
+            for (int ci = sub; ci < n_cand; ci += G) consider(ci);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, c1, o);
+                const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+                top2_insert_max(c1, c2, o1);
+                top2_insert_max(c1, c2, o2);
+            }
+        }
+        if (live && sub == 0) {
+            // (dot + 257) << 32 | ~local chunk  ->  (dot + 257) << 32 | ~first GLOBAL row of the chunk
+            auto globalise = [&](unsigned long long c) -> unsigned long long {
+                if (c == 0) return 0ull;
+                const unsigned gchunk = 0xFFFFFFFFu - (unsigned)(c & 0xFFFFFFFFull);
+                const unsigned first_row = (unsigned)(base + (long long)gchunk * p.chunk);
+                return (c & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - first_row);
+            };
+            s_keys[it * kQPB + (threadIdx.x >> 5) * kQPW + lane / G] = make_ulonglong2(globalise(c1), globalise(c2));
+        }
+    }
+    __syncthreads();
+    const int n_here = (int)max(0ll, min((long long)kQPB * iters, n_q - q_block));
+    bool wrote = false;
+    for (int i = threadIdx.x; i < n_here * ex.world; i += blockDim.x) {
+        const int r = i / n_here, k = i - r * n_here;
+        slm_exchange_store_chunks_to(ex, r, q_block + k, s_keys[k].x, s_keys[k].y);
+        wrote = true;
+    }
+    slm_exchange_publish(ex, wrote, 0);
+}
+
+__global__ void __launch_bounds__(256) tc_refine_owned_kernel(TcParams p, long long base, slm_exchange ex)
+{
+    constexpr int G = 8, kQPW = 4, kQPB = 32;
+    __shared__ ulonglong2 s_keys[kQPB];
+    slm_pdl_launch_dependents();
+    if (!slm_exchange_wait_flags(ex, 0)) return;          // a lost peer: reported; this rank publishes nothing either
+    const int lane = threadIdx.x & 31, sub = lane % G;
+    const long long n_q = p.nq;
+    bool wrote = false;
+    for (long long q0 = (long long)blockIdx.x * kQPB; q0 < n_q; q0 += (long long)gridDim.x * kQPB) {
+        const long long gq = q0 + (threadIdx.x >> 5) * kQPW + lane / G;
+        const bool live = gq < n_q;
+        const long long gqc = live ? gq : 0;
+        // the global best two chunks of this query out of every rank's two
+        unsigned long long c1 = 0, c2 = 0;
+        for (int i = sub; i < 2 * ex.world; i += G) {
+            unsigned long long c;
+            if (ex.key_bytes == 4) {
+                const unsigned *g = reinterpret_cast<const unsigned *>(ex.peer_keys[ex.rank]) + (slm_exchange_slot(ex, 0, i >> 1) + gqc) * 2;
+                c = slm_chunk_widen(g[i & 1]);
+            } else {
+                const unsigned long long *g = reinterpret_cast<const unsigned long long *>(ex.peer_keys[ex.rank]) +
+                                              (slm_exchange_slot(ex, 0, i >> 1) + gqc) * 2;
+                c = g[i & 1];
+            }
+            top2_insert_max(c1, c2, c);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, c1, o);
+            const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+            top2_insert_max(c1, c2, o1);
+            top2_insert_max(c1, c2, o2);
+        }
+        const unsigned fa = c1 ? 0xFFFFFFFFu - (unsigned)(c1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+        const unsigned fb = c2 ? 0xFFFFFFFFu - (unsigned)(c2 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+        const unsigned flo = min(fa, fb), fhi = max(fa, fb);         // first global rows; 0xFFFFFFFF = no such chunk
+        const uint4 *qs = reinterpret_cast<const uint4 *>(p.q + gqc * 8);
+        const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
+        unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const unsigned f = s == 0 ? flo : fhi;
+            // only the owner of a chunk re-scores it
+            if (f == 0xFFFFFFFFu || (long long)f < base || (long long)f >= base + p.nt) continue;
+            const long long row0 = (long long)f - base;
+            for (int pos = sub; pos < p.chunk; pos += G) {
+                const long long row = row0 + pos;
+                if (row < p.nt) {
+                    const uint4 *ts = reinterpret_cast<const uint4 *>(p.t + row * 8);
+                    const unsigned key = refine_key(hamming256(qa, qb, __ldg(ts), __ldg(ts + 1)), s, pos);
+                    const unsigned m = max(k1, key);
+                    k1 = min(k1, key);
+                    k2 = min(k2, m);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const unsigned o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o);
+            const unsigned o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
+            unsigned m = max(k1, o1);
+            k1 = min(k1, o1);
+            k2 = min(min(k2, o2), m);
+        }
+        if (live && sub == 0) {
+            auto widen = [&](unsigned k) -> unsigned long long {
+                if (k == 0xFFFFFFFFu) return kKeyNone;
+                return ((unsigned long long)(k >> 8) << 32) | (unsigned long long)(((k & 128u) ? fhi : flo) + (k & 127u));
+            };
+            s_keys[(threadIdx.x >> 5) * kQPW + lane / G] = make_ulonglong2(widen(k1), widen(k2));
+        }
+        __syncthreads();
+        const int n_here = (int)min((long long)kQPB, n_q - q0);
+        for (int i = threadIdx.x; i < n_here * ex.world; i += blockDim.x) {
+            const int r = i / n_here, k = i - r * n_here;
+            slm_exchange_store_to(ex, r, q0 + k, s_keys[k].x, s_keys[k].y, 1);
+            wrote = true;
+        }
+        __syncthreads();
+    }
+    slm_exchange_publish(ex, wrote, 1);
 }
 
 // Refine for batches of frame-sized problems (config 3).  tc_refine_kernel reads every query's candidate rows
@@ -861,7 +1022,8 @@ long long plan_cpg(const slm_ctx *ctx, long long units, long long n_tiles, doubl
 }
 
 int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_out, cudaStream_t stream,
-           const slm_exchange *exchange = nullptr, const slm_chain *chain = nullptr, bool allow_fp4 = true)
+           const slm_exchange *exchange = nullptr, const slm_chain *chain = nullptr, bool allow_fp4 = true,
+           int *phase_out = nullptr)
 {
     p.n_prob = n_prob;
     const int m_tiles = (p.nq + kTileM - 1) / kTileM;
@@ -975,6 +1137,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     SLM_TRY(slm_buf_reserve(ctx, &ctx->scratch, cand_bytes));
     p.cand = reinterpret_cast<float2 *>(ctx->scratch.p);
 
+    if (phase_out) *phase_out = 0;
     ctx->last_kernel = fp4 ? "knn2_tc4_kernel" : two_cta ? "knn2_tc2_kernel" : "knn2_tc_kernel";
     SLM_TRY(slm_prof_begin(ctx, stream));
     if (fp4) {
@@ -1007,6 +1170,22 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         SLM_TRY(configure_smem(tc_refine_frame_kernel, configured, 200 * 1024));
         SLM_CUDA(slm_launch(tc_refine_frame_kernel, dim3((unsigned)n_prob), dim3(kRefineFrameThreads), frame_smem, stream, pdl, p,
                             reinterpret_cast<unsigned long long *>(keys_out)));
+    } else if (exchange && p.desc == nullptr && ctx->exchange_two_phase_min > 0 &&
+               n_q >= ctx->exchange_two_phase_min) {
+        // sharded, many queries: agree on the global best two chunks first, only their owners refine them
+        const bool few = p.cpg * p.n_epochs * 4 <= 32;
+        const int iters = n_q >= 65536 ? kRefineMaxIters : 1;
+        if (few)
+            SLM_CUDA(slm_launch(tc_chunk_keys_kernel<8>, dim3((unsigned)((n_q + 32 * iters - 1) / (32 * iters))), dim3(256), 0, stream,
+                                pdl, p, base, ex, iters));
+        else
+            SLM_CUDA(slm_launch(tc_chunk_keys_kernel<32>, dim3((unsigned)((n_q + 8 * iters - 1) / (8 * iters))), dim3(256), 0, stream,
+                                pdl, p, base, ex, iters));
+        long long blocks = (n_q + 31) / 32, cap = 4 * ctx->exchange_max_blocks;
+        if (blocks > cap) blocks = cap;
+        SLM_CUDA(slm_launch(tc_refine_owned_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, pdl, p, base, ex));
+        ctx->launches += 1;
+        if (phase_out) *phase_out = 1;
     } else if (p.cpg * p.n_epochs * 4 <= 32) {   // few candidates per query (many queries, short train sets): 8 lanes each
         // sharded path with many queries: 8 groups of 32 queries per block (one fence + one counter update per 256 queries)
         const int iters = (exchange && n_q >= 65536) ? kRefineMaxIters : 1;
@@ -1032,12 +1211,12 @@ int slm_tc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t
 }
 
 int slm_tc_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
-                         const slm_exchange &ex, cudaStream_t stream, bool fp4)
+                         const slm_exchange &ex, cudaStream_t stream, bool fp4, int *phase_out)
 {
     TcParams p{};
     p.q = q; p.t = t; p.desc = nullptr; p.pairs = nullptr; p.frame_words = 0;
     p.nq = (int)nq; p.nt = (int)nt;
-    return tc_run(ctx, p, 1, base, nullptr, stream, &ex, nullptr, fp4);
+    return tc_run(ctx, p, 1, base, nullptr, stream, &ex, nullptr, fp4, phase_out);
 }
 
 int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,

@@ -176,6 +176,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
     tc::tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
+    // The TMA producer (lane 0 of the first expander warp) requests its first raw half tiles NOW, so that the HBM latency of
+    // the first train tiles hides behind the expansion of the query tiles (matters on the sharded path, where a launch
+    // lasts ~0.2 ms).
+    const uint32_t sRaw_addr0 = tc::smem_u32(sRaw);
+    auto valid_rows = [&](int tile) { return max(0, min(kHalf, p.nt - (tile * tc4::kTileN + (int)rank * kHalf))); };
+    auto produce = [&](const TileIter &pi_, int slot) {
+        const int tile = pi_.r * p.range_tiles + pi_.bt;
+        const int v = valid_rows(tile);
+        if (v > 0) {
+            mbar_arrive_expect_tx(&bars->raw_full[slot], (uint32_t)v * 32);
+            bulk_copy_g2s(sRaw_addr0 + (uint32_t)slot * kRawBytes, t + ((long long)tile * tc4::kTileN + (long long)rank * kHalf) * 8,
+                          (uint32_t)v * 32, &bars->raw_full[slot]);
+        } else {
+            tc::mbar_arrive(&bars->raw_full[slot]);
+        }
+    };
+    TileIter pi;                                             // producer position: kRawStages tiles ahead of the expanders
+    iter_start(pi, p, unit, total_tiles);
+    if (tid == kEpiThreads) {
+        for (int s = 0; s < kRawStages && !pi.done; ++s) {
+            produce(pi, s);
+            iter_next(pi, p, total_tiles);
+        }
+    }
+
     // scale factors: every byte of columns [480, 512) = UE8M0 1.0, in both CTAs (4 warps = 128 lanes)
     if (warp < 4) tc4::tmem_fill32(tmem + ((uint32_t)(warp * 32) << 16) + tc4::kSfCol, tc4::kScaleOnes);
 
@@ -310,27 +335,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
         const int et = tid - kEpiThreads;   // 0..95
         const uint32_t sB_addr = tc::smem_u32(sB), sRaw_addr = tc::smem_u32(sRaw);
         const bool two_rows = et < kHalf - kExpThreads;          // threads 0..23 also expand row 96 + et
-        // rows of this CTA's half of `tile` that exist
-        auto valid_rows = [&](int tile) { return max(0, min(kHalf, p.nt - (tile * tc4::kTileN + (int)rank * kHalf))); };
-        auto produce = [&](const TileIter &pi, int slot) {
-            const int tile = pi.r * p.range_tiles + pi.bt;
-            const int v = valid_rows(tile);
-            if (v > 0) {
-                mbar_arrive_expect_tx(&bars->raw_full[slot], (uint32_t)v * 32);
-                bulk_copy_g2s(sRaw_addr + (uint32_t)slot * kRawBytes, t + ((long long)tile * tc4::kTileN + (long long)rank * kHalf) * 8,
-                              (uint32_t)v * 32, &bars->raw_full[slot]);
-            } else {
-                tc::mbar_arrive(&bars->raw_full[slot]);
-            }
-        };
-        TileIter pi;                                             // producer runs kRawStages tiles ahead
-        iter_start(pi, p, unit, total_tiles);
-        if (et == 0) {
-            for (int s = 0; s < kRawStages && !pi.done; ++s) {
-                produce(pi, s);
-                iter_next(pi, p, total_tiles);
-            }
-        }
         int sb = 0, phb = 0, sr = 0, phr = 0;
         TileIter it;
         for (iter_start(it, p, unit, total_tiles); !it.done; iter_next(it, p, total_tiles)) {

@@ -53,6 +53,9 @@ struct slm_ctx {
     int *exchange_status = nullptr;     // mapped pinned int[4]: (code, rank, step, value seen) written by the merge kernel
     long long exchange_max_blocks = 296;   // grid cap of the wait + merge kernel (SLM_EXCHANGE_MAX_BLOCKS; loopback tests lower it)
     unsigned exchange_max_polls = 1u << 23;   // flag polls before a peer is reported lost (~4 s; SLM_EXCHANGE_MAX_POLLS)
+    long long exchange_two_phase_min = 32768; // sharded tensor path: from this many queries on, the ranks first agree on every
+                                              // query's GLOBAL best two candidate chunks and only their owners refine them
+                                              // (SLM_EXCHANGE_TWO_PHASE_MIN; 0 = never)
     int exchange_wide_keys = 0;         // SLM_EXCHANGE_WIDE_KEYS: always exchange 64-bit keys (A/B of the compact form)
     // stream bookkeeping: every device entry point runs between slm_enter() and slm_leave()
     cudaStream_t cur_stream = nullptr;  // stream of the call in progress (workspace growth is ordered on it)
@@ -168,7 +171,9 @@ int slm_compact(slm_ctx *ctx, const int32_t *idx, const int32_t *dist, const uin
                 int32_t stop_at_short_row, int32_t *matches_out, int32_t *count_out, cudaStream_t stream);
 
 // ---- NVLink exchange of per-rank keys (sharded path; protocol in exchange.cuh) --------------------------------
-// Every rank's key buffer [2][world][cap][2] keys and flag array uint32[2][world] are peer-mapped on this GPU.
+// Every rank's key buffer [2 phases][2 halves][world][cap][2] keys and flag array uint32[2][2][world] are peer-mapped on
+// this GPU.  Phase 0 carries what the first kernel of a step produces (the exact keys, or -- two-phase form for many
+// queries -- the candidate-chunk keys), phase 1 the exact keys of the two-phase form.
 static constexpr int kSlmMaxWorld = 16;
 struct slm_exchange {
     unsigned char *peer_keys[kSlmMaxWorld];
@@ -178,13 +183,15 @@ struct slm_exchange {
     long long cap;
     int key_bytes;            // 8: uint64 keys (distance << 32 | index); 4: compact uint32 keys (distance << 16 | index)
     unsigned *done_counter;   // device counter for the last-block-done pattern (zero between launches)
+    unsigned max_polls;       // flag polls before a peer is reported lost
+    int *status;              // mapped host int[4]: (code, rank, step, value seen), written on a timeout
 };
 int slm_exchange_setup(slm_ctx *ctx, slm_exchange *ex, const uint64_t *peer_keys_host, const uint64_t *peer_flags_host,
                        int32_t rank, int32_t world, uint32_t step, int64_t cap, int64_t nt_global);
 // producer for keys that already sit in local memory (non-tensor variants)
 int slm_exchange_store(slm_ctx *ctx, const slm_exchange &ex, const uint64_t *local_keys, int64_t nq, cudaStream_t stream);
 // wait for every rank's keys of this step, merge, finalise
-int slm_exchange_wait_merge(slm_ctx *ctx, const slm_exchange &ex, int64_t nq, int32_t ratio_num, int32_t ratio_den,
+int slm_exchange_wait_merge(slm_ctx *ctx, const slm_exchange &ex, int phase, int64_t nq, int32_t ratio_num, int32_t ratio_den,
                             int32_t *idx_out, int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
 // SLM_ERR_TIMEOUT if an earlier merge kernel reported a lost peer (clears the report)
 int slm_exchange_check(slm_ctx *ctx);
@@ -195,8 +202,9 @@ int slm_tc_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t
                      int64_t base, uint64_t *keys_out, cudaStream_t stream, bool fp4);
 // Search + NVLink exchange: the refine kernel stores each query's keys straight into every peer's buffer and its
 // last block publishes the flags (the caller follows with slm_exchange_wait_merge).
+// *phase_out = the exchange phase whose keys the caller's wait + merge must read (1 after the two-phase form)
 int slm_tc_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
-                         const slm_exchange &ex, cudaStream_t stream, bool fp4);
+                         const slm_exchange &ex, cudaStream_t stream, bool fp4, int *phase_out);
 // Chained batch (config 3): the caller's pairs sorted by query frame and cut into units of pairs that share it
 // (all device arrays; see TcParams in knn2_tc.cu).  Optional: nullptr = every pair is its own launch item.
 struct slm_chain {

@@ -387,10 +387,14 @@ __device__ __forceinline__ void tmem_fill32(uint32_t taddr, uint32_t v)
 // bits of its eight nibbles (the K permutation is shared by both operands): 1 shift + 1 LOP3 per 8 values.
 __device__ __forceinline__ void expand_word_to_smem(uint32_t addr, uint32_t w)
 {
-    const uint32_t o0 = (w & 0x88888888u) | kE2m1PlusOne;
-    const uint32_t o1 = ((w << 1) & 0x88888888u) | kE2m1PlusOne;
-    const uint32_t o2 = ((w << 2) & 0x88888888u) | kE2m1PlusOne;
-    const uint32_t o3 = ((w << 3) & 0x88888888u) | kE2m1PlusOne;
+    // (x & 0x88888888) | 0x22222222 as ONE LOP3 (LUT 0xEA = (a & b) | c) with both constants in registers; written as C the
+    // two different immediates cost two LOP3 per word
+    uint32_t o0, o1, o2, o3;
+    const uint32_t m = 0x88888888u, c = kE2m1PlusOne;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(o0) : "r"(w), "r"(m), "r"(c));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(o1) : "r"(w << 1), "r"(m), "r"(c));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(o2) : "r"(w << 2), "r"(m), "r"(c));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(o3) : "r"(w << 3), "r"(m), "r"(c));
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
 }
 // byte offset of (row, K-chunk) inside an operand tile

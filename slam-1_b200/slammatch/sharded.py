@@ -12,6 +12,8 @@ Exchanges (``exchange=``):
   ``nvlink``  peer stores over NVLink / NVSwitch into torch symmetric memory + flags + merge kernel
               (slm_knn2_exchange: the tensor path's refine kernel is the producer).  Keys travel as 32-bit words
               ``distance << 16 | index`` when the whole train set has at most 65 536 rows (config 4's vocabulary).
+              From 32 768 queries on, the ranks first exchange candidate-chunk keys and only the owner of a query's
+              global best two chunks re-scores them exactly -- the re-scoring is shared, not repeated on every rank.
   ``nccl``    all-gather of the packed keys + slm_merge_top2 (the form north_star names; also the CPU / gloo form).
   ``a2a``     all-to-all of query slices + per-rank merge + all-gather of the merged results.
   ``auto``    nvlink when every rank can set it up (the ranks agree through an all-reduce), else nccl.
@@ -122,8 +124,9 @@ class ShardedMatcher:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = self.group if self.group is not None else dist.group.WORLD
-        keys = symm_mem.empty((2, self.world, cap, 2), dtype=torch.int64, device=device)
-        flags = symm_mem.empty((2 * self.world,), dtype=torch.int32, device=device)
+        # [2 phases][2 halves][world][cap][2] keys, uint32[2][2][world] flags (include/slammatch.h)
+        keys = symm_mem.empty((4, self.world, cap, 2), dtype=torch.int64, device=device)
+        flags = symm_mem.empty((4 * self.world,), dtype=torch.int32, device=device)
         flags.zero_()
         hk = symm_mem.rendezvous(keys, group)
         hf = symm_mem.rendezvous(flags, group)

@@ -38,8 +38,9 @@ class _Ranks:
                 os.environ["SLM_EXCHANGE_MAX_BLOCKS"] = old
         self.world, self.cap = world, cap
         self.streams = [torch.cuda.Stream() for _ in range(world)]
-        self.keys = [torch.zeros((2, world, cap, 2), dtype=torch.int64, device="cuda") for _ in range(world)]
-        self.flags = [torch.zeros((2 * world,), dtype=torch.int32, device="cuda") for _ in range(world)]
+        # [2 phases][2 halves][world][cap][2] keys and uint32[2][2][world] flags per rank (include/slammatch.h)
+        self.keys = [torch.zeros((4, world, cap, 2), dtype=torch.int64, device="cuda") for _ in range(world)]
+        self.flags = [torch.zeros((4 * world,), dtype=torch.int32, device="cuda") for _ in range(world)]
         arr = ctypes.c_uint64 * world
         self.key_ptrs = arr(*[k.data_ptr() for k in self.keys])
         self.flag_ptrs = arr(*[f.data_ptr() for f in self.flags])
@@ -56,8 +57,8 @@ class _Ranks:
         'rank' whose merge kernel is polling for this rank's flags.  (No issue across real GPUs: one process per device.)"""
         import torch
         nq = q_dev.shape[0]
-        keys = torch.zeros((2, 1, self.cap, 2), dtype=torch.int64, device="cuda")
-        flags = torch.zeros((2,), dtype=torch.int32, device="cuda")
+        keys = torch.zeros((4, 1, self.cap, 2), dtype=torch.int64, device="cuda")
+        flags = torch.zeros((4,), dtype=torch.int32, device="cuda")
         kp, fp = (ctypes.c_uint64 * 1)(keys.data_ptr()), (ctypes.c_uint64 * 1)(flags.data_ptr())
         idx = torch.empty((nq, 2), dtype=torch.int32, device="cuda")
         ctx = self.ctxs[0]
@@ -143,12 +144,14 @@ def test_loopback_exchange_equals_oracle_64bit_keys(world, variant):
         ranks.close()
 
 
-@pytest.mark.parametrize("world,nq", [(2, 20_000), (8, 20_000), (2, 70_000)])
+@pytest.mark.parametrize("world,nq", [(2, 20_000), (8, 20_000), (2, 70_000), (4, 40_000)])
 @pytest.mark.parametrize("variant", ["auto", "tensor"])
 def test_loopback_exchange_config4_regime_32bit_keys(world, nq, variant):
     """Config 4 in miniature: many queries (above the old 8192 cap), a vocabulary of at most 65 536 words sharded by rows
-    -> compact 32-bit keys (distance << 16 | word), merge kernel with a capped grid.  70 000 queries reach the refine
-    kernel's multi-group blocks (8 x 32 queries per block, one fence per block) that config 4 itself runs with."""
+    -> compact 32-bit keys (distance << 16 | word), merge kernel with a capped grid.  From 32 768 queries on the tensor path
+    takes the two-phase form config 4 itself runs with: candidate-chunk keys are exchanged first and only the owner of a
+    query's global best two chunks re-scores them (tc_chunk_keys_kernel / tc_refine_owned_kernel); 70 000 queries also
+    reach the multi-group blocks (8 x 32 queries per block, one fence per block)."""
     import torch
     nt = 48_000 if nq <= 20_000 else 30_000
     ranks = _Ranks(world, cap=1 << (nq - 1).bit_length())
