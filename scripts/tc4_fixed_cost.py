@@ -16,13 +16,16 @@ for nt in (17_760, 88_800, 177_600, 355_200, 710_400, 1_250_000, 2_500_000):
     for _ in range(5):
         slammatch.knn2(q, t, variant=variant)
     torch.cuda.synchronize()
-    ctx.profile(True); ctx.profile_read()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 50
     e0.record()
     for _ in range(n):
         slammatch.knn2(q, t, variant=variant)
     e1.record(); torch.cuda.synchronize()
+    ctx.profile(True); ctx.profile_read()          # kernel time in a separate pass: the event records serialise the launches
+    for _ in range(n):
+        slammatch.knn2(q, t, variant=variant)
+    torch.cuda.synchronize()
     km, kn = ctx.profile_read(); ctx.profile(False)
     tiles = -(-nt // 240)
     print(f"{variant} nt={nt:8d} tiles/cluster={tiles/74:6.1f}  kernel {km/kn*1e3:8.1f} us  call {e0.elapsed_time(e1)/n*1e3:8.1f} us  "

@@ -211,6 +211,7 @@ int slm_create(int device, slm_ctx **ctx_out)
         if (v >= 1) ctx->exchange_max_blocks = v;
     }
     if (const char *e = getenv("SLM_EXCHANGE_TWO_PHASE_MIN")) ctx->exchange_two_phase_min = atoll(e);
+    if (const char *e = getenv("SLM_EXCHANGE_TWO_PHASE_WORLD")) ctx->exchange_two_phase_world = atoi(e);
     if (const char *e = getenv("SLM_EXCHANGE_MAX_POLLS")) {
         long long v = atoll(e);
         if (v >= 1 && v <= 0xFFFFFFFFll) ctx->exchange_max_polls = (unsigned)v;

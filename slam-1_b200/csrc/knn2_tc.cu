@@ -1170,8 +1170,8 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         SLM_TRY(configure_smem(tc_refine_frame_kernel, configured, 200 * 1024));
         SLM_CUDA(slm_launch(tc_refine_frame_kernel, dim3((unsigned)n_prob), dim3(kRefineFrameThreads), frame_smem, stream, pdl, p,
                             reinterpret_cast<unsigned long long *>(keys_out)));
-    } else if (exchange && p.desc == nullptr && ctx->exchange_two_phase_min > 0 &&
-               n_q >= ctx->exchange_two_phase_min) {
+    } else if (exchange && p.desc == nullptr && ctx->exchange_two_phase_min > 0 && n_q >= ctx->exchange_two_phase_min &&
+               (exchange->world >= ctx->exchange_two_phase_world || exchange->world == 1)) {
         // sharded, many queries: agree on the global best two chunks first, only their owners refine them
         const bool few = p.cpg * p.n_epochs * 4 <= 32;
         const int iters = n_q >= 65536 ? kRefineMaxIters : 1;

@@ -299,6 +299,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
                         tc::tmem_pin32(Z);
                         tc::tmem_pin8(Z + 32);
                         tc::tc_fence_before();
+                        // (one arrival per THREAD: a per-warp arrival behind __syncwarp measured 7 % slower per tile,
+                        // profiles/r2_tc4_fixed_cost_v2_warp_arrive.txt)
                         tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
                         const float mx1 = fmaxf(max_cols<32>(Y), max_cols<8>(Y + 32));
                         const float mx2 = fmaxf(max_cols<32>(Z), max_cols<8>(Z + 32));

@@ -56,6 +56,8 @@ struct slm_ctx {
     long long exchange_two_phase_min = 32768; // sharded tensor path: from this many queries on, the ranks first agree on every
                                               // query's GLOBAL best two candidate chunks and only their owners refine them
                                               // (SLM_EXCHANGE_TWO_PHASE_MIN; 0 = never)
+    int exchange_two_phase_world = 4;         // ... and only from this many ranks on: with 2 ranks the second exchange round
+                                              // costs more than the halved refine saves (SLM_EXCHANGE_TWO_PHASE_WORLD)
     int exchange_wide_keys = 0;         // SLM_EXCHANGE_WIDE_KEYS: always exchange 64-bit keys (A/B of the compact form)
     // stream bookkeeping: every device entry point runs between slm_enter() and slm_leave()
     cudaStream_t cur_stream = nullptr;  // stream of the call in progress (workspace growth is ordered on it)

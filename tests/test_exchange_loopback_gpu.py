@@ -26,16 +26,19 @@ class _Ranks:
 
     def __init__(self, world, cap):
         import torch
-        old = os.environ.get("SLM_EXCHANGE_MAX_BLOCKS")
-        # few polling blocks per rank: the other ranks' search kernels need whole SMs of the same GPU to make progress
-        os.environ["SLM_EXCHANGE_MAX_BLOCKS"] = "8"
+        # few polling blocks per rank: the other ranks' search kernels need whole SMs of the same GPU to make progress;
+        # the two-phase form from 2 ranks on (the default, 4, is a measured crossover, not a correctness limit)
+        env = {"SLM_EXCHANGE_MAX_BLOCKS": "8", "SLM_EXCHANGE_TWO_PHASE_WORLD": "2"}
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
         try:
             self.ctxs = [_lib.Context(0) for _ in range(world)]
         finally:
-            if old is None:
-                del os.environ["SLM_EXCHANGE_MAX_BLOCKS"]
-            else:
-                os.environ["SLM_EXCHANGE_MAX_BLOCKS"] = old
+            for k, v in old.items():
+                if v is None:
+                    del os.environ[k]
+                else:
+                    os.environ[k] = v
         self.world, self.cap = world, cap
         self.streams = [torch.cuda.Stream() for _ in range(world)]
         # [2 phases][2 halves][world][cap][2] keys and uint32[2][2][world] flags per rank (include/slammatch.h)
