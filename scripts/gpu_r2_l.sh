@@ -1,8 +1,8 @@
 #!/bin/bash
-# Round 2 (2 GPUs): per-warp barrier arrivals + bench profile pass: parity subset, fixed cost, c5 / c4 at 1 and 2 ranks (c4 two-phase exchange).
+# Round 2 (1 GPU): tc4 v6 (jobs issued as two half-N MMA chains): parity, fixed cost, c5 / c4.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_config4_regime_gpu.py tests/test_exchange_loopback_gpu.py tests/test_multi_gpu.py -q -m gpu > gpurun_out/pytest_sel.txt 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_sel.txt
+timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_config4_regime_gpu.py tests/test_exchange_loopback_gpu.py tests/test_frame_gpu.py -q -m gpu > gpurun_out/pytest_sel.txt 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_sel.txt
 timeout 300 python scripts/tc4_fixed_cost.py tensor4 2>&1 | tee gpurun_out/tc4_fixed_cost.txt
 run() {  # n, tag, extra args
   local n=$1; shift; local tag=$1; shift
@@ -23,5 +23,3 @@ except Exception as e:
 PY
 }
 run 1 auto
-run 2 auto
-SLM_EXCHANGE_TWO_PHASE_MIN=0 run 2 onephase

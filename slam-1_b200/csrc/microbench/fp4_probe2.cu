@@ -140,6 +140,28 @@ probe2_kernel(const uint4 *a_bits, const uint4 *b_bits, float *d_out, long long 
 
     long long t0 = clock64();
     const int mma_loops = mode == 1 ? loops : 1;
+    if (mode == 6 || mode == 7) {
+        // mode 6: every 240-column job as TWO chains with different shapes (N = 128 then N = 112), as knn2_tc4_kernel v6 issued
+        // them; mode 7: the same two chains with ONE shape (N = 112 twice).  Does alternating instruction descriptors cost?
+        if (rank == 0 && tid == 0) {
+            const uint32_t i0 = idesc_mxf4(2 * kM, mode == 6 ? 128 : 112), i1 = idesc_mxf4(2 * kM, 112);
+            for (int l = 0; l < loops; ++l) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = tc::smem_desc(tc::smem_u32(sa) + k * 2 * kLBO4, kLBO4, kSBO4);
+                    const uint64_t bd = tc::smem_desc(tc::smem_u32(sb) + k * 2 * kLBO4, kLBO4, kSBO4);
+                    umma_mxf4_2cta(tmem + (l & 1) * 240, ad, bd, i0, k > 0 ? 1u : 0u, sf, sf);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = tc::smem_desc(tc::smem_u32(sa) + k * 2 * kLBO4, kLBO4, kSBO4);
+                    const uint64_t bd = tc::smem_desc(tc::smem_u32(sb) + 8 * kSBO4 + k * 2 * kLBO4, kLBO4, kSBO4);
+                    umma_mxf4_2cta(tmem + (l & 1) * 240 + 128, ad, bd, i1, k > 0 ? 1u : 0u, sf, sf);
+                }
+            }
+            tc::umma_commit_2cta(&ps->bar, 3);
+        }
+    } else
     if (rank == 0 && tid == 0) {
         for (int l = 0; l < mma_loops; ++l) {
 #pragma unroll
@@ -277,6 +299,17 @@ int main(int argc, char **argv)
         printf("mxf4 2cta mma: loops %d  median %lld cyc => %.0f MAC/clk/SM, %.1f clk per 256x%dx256 job; kernel %.3f ms => %.2f Tcmp/s, %.0f TFLOP/s\n",
                loops, c[c.size() / 2], macs_per_sm / c[c.size() / 2], (double)c[c.size() / 2] / loops, N, ms,
                (double)loops * kM * N * grid / (ms * 1e-3) / 1e12, 2.0 * macs_per_sm * grid / (ms * 1e-3) / 1e12);
+    }
+    for (int mode : {6, 7}) {
+        const int loops = 2048;
+        probe2_kernel<<<grid, kThreads, smem>>>(da, db, dd, dc, mode, loops, N, sf_col);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hc.data(), dc, hc.size() * 8, cudaMemcpyDeviceToHost));
+        std::vector<long long> c;
+        for (int s = 0; s < grid; s += 2) c.push_back(hc[s * 4]);
+        std::sort(c.begin(), c.end());
+        printf("split job, %s: %.1f clk per job (N = %d columns in two chains)\n", mode == 6 ? "N=128 then N=112 (two shapes)" : "N=112 twice (one shape)",
+               (double)c[c.size() / 2] / loops, mode == 6 ? 240 : 224);
     }
     {
         const int loops = 2048;

@@ -11,8 +11,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 # (name, nq, nt, seed): config-5-like (few queries, long DB, 64-bit keys) and config-4-like (many queries, <= 65536 words,
-# 32-bit keys on the NVLink exchange)
-CASES = [("c5like", 512, 300_000, 17), ("c4like", 20_000, 60_000, 19)]
+# 32-bit keys on the NVLink exchange; two-phase refine from 4 ranks on)
+CASES = [("c5like", 512, 300_000, 17), ("c4like", 40_000, 60_000, 19)]
 
 
 def _free_port():
