@@ -205,6 +205,7 @@ int slm_create(int device, slm_ctx **ctx_out)
         if (v == 120 || v == 40) ctx->tc4_chunk = v;
     }
     ctx->no_pdl = getenv("SLM_NO_PDL") != nullptr;
+    ctx->tc4_timing = getenv("SLM_TC4_TIMING") != nullptr;
     ctx->exchange_max_blocks = 2ll * prop.multiProcessorCount;
     if (const char *e = getenv("SLM_EXCHANGE_MAX_BLOCKS")) {
         long long v = atoll(e);

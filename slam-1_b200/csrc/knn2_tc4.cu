@@ -44,6 +44,9 @@ constexpr int kBStages = 3;                          // expanded half tiles (15 
 constexpr int kRawStages = 4;                        // raw packed half tiles (3840 B each)
 constexpr uint32_t kRawBytes = tc4::kHalfN * 32;
 constexpr int kHalf = tc4::kHalfN;                   // 120
+#ifndef SLM_TC4_FENCE_BEFORE_HANDBACK
+#define SLM_TC4_FENCE_BEFORE_HANDBACK 1              // A/B switch (compile time): no measurable cost, kept
+#endif
 
 struct Bars4 {
     uint64_t a_full;
@@ -109,6 +112,8 @@ __device__ __forceinline__ void mbar_wait_lean(uint64_t *bar, uint32_t parity)
                  "@!p bra WAIT_%=;\n\t}" ::"r"(tc::smem_u32(bar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void pin_timing(float &x) { asm volatile("" : "+f"(x) :: "memory"); }
+
 template <int C>
 __device__ __forceinline__ float max_cols(const uint32_t *v)
 {
@@ -127,7 +132,9 @@ __device__ __forceinline__ float max_cols(const uint32_t *v)
     return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-template <int CH>
+// TIMING (diagnostic build of the same kernel, SLM_TC4_TIMING=1): two epilogue warps and the MMA warp of cluster 0 sum
+// clock64 intervals per phase and write them to p.timing -- where a job's 597 clk go.
+template <int CH, bool TIMING>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(TcParams p)
 {
     static_assert(CH == 120 || CH == 40, "candidate chunk width");
@@ -256,6 +263,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
         // nobody tracks its result.)
         const int mt_jobs = (mt_pair + 1) & ~1;
         int job = 0, epoch = 0, lt = 0, j = 0, last_r = -1;     // lt = tiles seen in this epoch, j = ranges walked
+        long long tm[5] = {0, 0, 0, 0, 0};                      // TIMING: wait full | loads 0+1 | reduce 0 + load 2 | reduce 1+2, track | jobs
+        long long tq = 0;
+        if constexpr (TIMING) tq = clock64();
         uint32_t X[40], Y[40], Z[40];        // three 40-column register buffers
         auto valid_cols_of = [&](const TileIter &ti) { return min(tc4::kTileN, p.nt - (ti.r * p.range_tiles + ti.bt) * tc4::kTileN); };
         TileIter it;
@@ -277,31 +287,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
                     const uint32_t acc = lane_addr + ab * tc4::kTileN;
                     const bool active = tile_active && m < mt_mine;
                     if (active) {
-                        // Three 40-column pieces: pieces 0 and 1 are requested together, piece 2 as soon as they have landed;
-                        // the accumulator is handed back when piece 2 has landed, i.e. after ONE reduction (piece 0), and the
-                        // TMEM read of piece 2 (128 x 240 x 4 B per job = 131 clk of TMEM bandwidth per SM) overlaps that
-                        // reduction.  Hand-back latency is what the MMA waits for with only two accumulators.
+                        // All 120 columns of this warp are requested at once (three 40-column pieces, 120 registers); they land
+                        // within ~40 clk and the accumulator is handed back BEFORE any reduction: with only two accumulators
+                        // the chain MMA -> commit -> TMEM read -> hand-back -> next MMA bounds the kernel, and the diagnostic
+                        // build (SLM_TC4_TIMING, profiles/r2_tc4_timing_*.txt) showed the reduction of piece 0 (190 clk with
+                        // both warps of a scheduler on the ALU pipe) sitting inside that chain.
                         mbar_wait_lean(&bars->acc_full[ab], ph);
                         tc::tc_fence_after();
+                        if constexpr (TIMING) { const long long c = clock64(); tm[0] += c - tq; tq = c; }
                         tc::tmem_ldx32(acc, X);
                         tc::tmem_ldx8(acc + 32, X + 32);
                         tc::tmem_ldx32(acc + 40, Y);
                         tc::tmem_ldx8(acc + 72, Y + 32);
+                        tc::tmem_ldx32(acc + 80, Z);
+                        tc::tmem_ldx8(acc + 112, Z + 32);
                         tc::tmem_wait_ld();
                         tc::tmem_pin32(X);
                         tc::tmem_pin8(X + 32);
                         tc::tmem_pin32(Y);
                         tc::tmem_pin8(Y + 32);
-                        tc::tmem_ldx32(acc + 80, Z);
-                        tc::tmem_ldx8(acc + 112, Z + 32);
-                        const float mx0 = fmaxf(max_cols<32>(X), max_cols<8>(X + 32));
-                        tmem_wait_ld_after(mx0);  // piece 0 is reduced while piece 2 is in flight
                         tc::tmem_pin32(Z);
                         tc::tmem_pin8(Z + 32);
-                        tc::tc_fence_before();
-                        // (one arrival per THREAD: a per-warp arrival behind __syncwarp measured 7 % slower per tile,
-                        // profiles/r2_tc4_fixed_cost_v2_warp_arrive.txt)
+                        if constexpr (TIMING) { const long long c = clock64(); tm[1] += c - tq; tq = c; }
+                        // One unconditional arrival per THREAD.  Measured alternatives, all 7-10 % slower per tile although they
+                        // send fewer / cheaper messages (any branch around the arrival changes ptxas's schedule of the
+                        // hand-back path): one arrival per warp behind __syncwarp; local arrivals for the leader CTA's own
+                        // threads.  Dropping the tcgen05.fence in front of it changes nothing (profiles/r2_tc4_epilogue_steps.txt).
+                        if (SLM_TC4_FENCE_BEFORE_HANDBACK) tc::tc_fence_before();
                         tc::mbar_arrive_cluster_relaxed(&bars->acc_empty[ab], 0);
+                        if constexpr (TIMING) { const long long c = clock64(); tm[2] += c - tq; tq = c; }
+                        const float mx0 = fmaxf(max_cols<32>(X), max_cols<8>(X + 32));
                         const float mx1 = fmaxf(max_cols<32>(Y), max_cols<8>(Y + 32));
                         const float mx2 = fmaxf(max_cols<32>(Z), max_cols<8>(Z + 32));
                         if constexpr (CH == 120) {
@@ -310,6 +325,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
                             track(b1[m], b2[m], fmaf(mx0, kKeyScale, bias0));
                             if (col0 + 40 < valid_cols) track(b1[m], b2[m], fmaf(mx1, kKeyScale, bias0 - 1.0f));
                             if (col0 + 80 < valid_cols) track(b1[m], b2[m], fmaf(mx2, kKeyScale, bias0 - 2.0f));
+                        }
+                        if constexpr (TIMING) {
+                            pin_timing(b1[m]);
+                            const long long c = clock64();
+                            tm[3] += c - tq;
+                            tq = c;
+                            tm[4] += 1;
                         }
                     } else {
                         // nothing to read for this warp (idle half of a pair, padding job, columns past the train set)
@@ -332,6 +354,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
             static_assert(kMaxMT4 == 8, "one_job is instantiated for m = 0..7");
         }
         for (; epoch < p.n_epochs; ++epoch) flush(epoch);     // remaining epochs are written as "none"
+        if constexpr (TIMING) {
+            if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4))
+                for (int k = 0; k < 5; ++k) p.timing[(warp >> 2) * 8 + k] = tm[k];
+        }
     } else if (warp < mma_warp) {
         // ===================== expanders + TMA producer: this CTA's half of every train tile =====================
         const int et = tid - kEpiThreads;   // 0..95
@@ -377,25 +403,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
             tc::tc_fence_after();
             const int mt_jobs = (mt_pair + 1) & ~1;
             int job = 0, s = 0, ph = 0;
+            long long tm[4] = {0, 0, 0, 0};      // TIMING: wait b_full | wait acc_empty | issue | jobs
+            long long tq = 0;
+            if constexpr (TIMING) tq = clock64();
             TileIter it;
             for (iter_start(it, p, unit, total_tiles); !it.done; iter_next(it, p, total_tiles)) {
                 tc::mbar_wait_cluster(&bars->b_full[s], ph, 31 + s);
                 tc::tc_fence_after();
+                if constexpr (TIMING) { const long long c = clock64(); tm[0] += c - tq; tq = c; }
                 const uint32_t b_lo = b_lo0 + s * (tc4::kBHalfBytes >> 4);
                 for (int m = 0; m < mt_jobs; ++m) {          // even: the padding job repeats the last query tile
                     const int ab = job & 1;
                     tc::mbar_wait_cluster(&bars->acc_empty[ab], ((job >> 1) & 1) ^ 1, 40 + ab);
                     tc::tc_fence_after();
+                    if constexpr (TIMING) { const long long c = clock64(); tm[1] += c - tq; tq = c; }
                     if (tc::elect_one()) {
                         tc4::umma_job(tmem + ab * tc4::kTileN, a_lo0 + min(m, mt_pair - 1) * (tc4::kATileBytes >> 4), b_lo, idesc, sf);
                         tc::umma_commit_2cta(&bars->acc_full[ab], 3);
                     }
                     __syncwarp();
+                    if constexpr (TIMING) { const long long c = clock64(); tm[2] += c - tq; tq = c; tm[3] += 1; }
                     ++job;
                 }
                 if (tc::elect_one()) tc::umma_commit_2cta(&bars->b_empty[s], 3);
                 __syncwarp();
                 if (++s == kBStages) { s = 0; ph ^= 1; }
+            }
+            if constexpr (TIMING) {
+                if (blockIdx.x == 0 && lane == 0)
+                    for (int k = 0; k < 4; ++k) p.timing[16 + k] = tm[k];
             }
         }
     }
@@ -405,7 +441,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
     if (warp == mma_warp) tc::tmem_dealloc_2cta(tmem, 512);
 }
 
-template <int CH>
+template <int CH, bool TIMING>
 int launch_tc4(const TcParams &p, int grid_y, cudaStream_t stream)
 {
     const size_t smem_max = (size_t)kMaxMT4 * tc4::kATileBytes + kBStages * tc4::kBHalfBytes + kRawStages * kRawBytes + sizeof(Bars4) + 64;
@@ -413,26 +449,47 @@ int launch_tc4(const TcParams &p, int grid_y, cudaStream_t stream)
     int dev = 0;
     SLM_CUDA(cudaGetDevice(&dev));
     if (!configured[dev & 63].load(std::memory_order_acquire)) {
-        SLM_CUDA(cudaFuncSetAttribute(knn2_tc4_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        SLM_CUDA(cudaFuncSetAttribute(knn2_tc4_kernel<CH, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         configured[dev & 63].store(true, std::memory_order_release);
     }
     const size_t smem = (size_t)p.mt * tc4::kATileBytes + kBStages * tc4::kBHalfBytes + kRawStages * kRawBytes + sizeof(Bars4) + 64;
     const int n_gpairs = (p.n_groups + 1) / 2;
     dim3 grid((unsigned)(2 * n_gpairs * p.cpg), (unsigned)grid_y);
-    knn2_tc4_kernel<CH><<<grid, kThreads4, smem, stream>>>(p);
+    knn2_tc4_kernel<CH, TIMING><<<grid, kThreads4, smem, stream>>>(p);
     SLM_CUDA(cudaGetLastError());
     return SLM_OK;
 }
 
 }  // namespace
 
-int slm_tc4_launch(slm_ctx *ctx, const tcp::TcParams &p, int grid_y, cudaStream_t stream)
+int slm_tc4_launch(slm_ctx *ctx, const tcp::TcParams &p_in, int grid_y, cudaStream_t stream)
 {
-    (void)ctx;
+    tcp::TcParams p = p_in;
     if (p.mt < 1 || p.mt > kMaxMT4) return slm_fail(SLM_ERR_INVALID, "tc4: %d query tiles per CTA", p.mt);
+    if (ctx->tc4_timing && p.chunk == 120) {
+        // diagnostic: per-phase cycle sums of cluster 0 (synchronous; SLM_TC4_TIMING=1)
+        long long *dev = nullptr, h[24] = {};
+        SLM_CUDA(cudaMalloc(&dev, sizeof(h)));
+        SLM_CUDA(cudaMemset(dev, 0, sizeof(h)));
+        p.timing = dev;
+        SLM_TRY((launch_tc4<120, true>(p, grid_y, stream)));
+        SLM_CUDA(cudaStreamSynchronize(stream));
+        SLM_CUDA(cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost));
+        SLM_CUDA(cudaFree(dev));
+        for (int w = 0; w < 2; ++w) {
+            const double n = h[w * 8 + 4] > 0 ? (double)h[w * 8 + 4] : 1.0;
+            fprintf(stderr, "tc4 timing, epilogue warp %d (set %d): %lld jobs; per job: wait acc_full %.0f | loads 0+1 %.0f | reduce 0 + load 2 + hand-back %.0f | "
+                    "reduce 1+2 + track %.0f clk (sum %.0f)\n", w * 4, w, h[w * 8 + 4], h[w * 8] / n, h[w * 8 + 1] / n, h[w * 8 + 2] / n, h[w * 8 + 3] / n,
+                    (h[w * 8] + h[w * 8 + 1] + h[w * 8 + 2] + h[w * 8 + 3]) / n);
+        }
+        const double n = h[19] > 0 ? (double)h[19] : 1.0;
+        fprintf(stderr, "tc4 timing, MMA warp: %lld jobs; per job: wait b_full %.0f | wait acc_empty %.0f | issue %.0f clk (sum %.0f)\n", h[19],
+                h[16] / n, h[17] / n, h[18] / n, (h[16] + h[17] + h[18]) / n);
+        return SLM_OK;
+    }
     switch (p.chunk) {
-    case 120: return launch_tc4<120>(p, grid_y, stream);
-    case 40: return launch_tc4<40>(p, grid_y, stream);
+    case 120: return launch_tc4<120, false>(p, grid_y, stream);
+    case 40: return launch_tc4<40, false>(p, grid_y, stream);
     default: return slm_fail(SLM_ERR_INVALID, "tc4: unsupported candidate chunk width %d", p.chunk);
     }
 }

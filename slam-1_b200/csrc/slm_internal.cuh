@@ -66,6 +66,7 @@ struct slm_ctx {
     bool have_last = false;
     int tc_fp4 = 1;                     // AUTO uses the mxf4 tensor kernel where it applies (SLM_TC_FP4=0: fp8 only)
     int tc4_chunk = 0;                  // SLM_TC4_CHUNK: force the fp4 kernel's candidate chunk width (120 or 40; tests / A-B)
+    int tc4_timing = 0;                 // SLM_TC4_TIMING: run the diagnostic build of the mxf4 kernel and print per-phase cycles
     int no_pdl = 0;                     // SLM_NO_PDL: launch the refine / merge kernels without programmatic dependent launch
     int profile = 0;
     static constexpr int kMaxProf = 4096;

@@ -38,6 +38,7 @@ struct TcParams {
     const int32_t *chain_pairs;   // device int32[n_prob][2], pairs sorted by query frame (nullptr = not chained)
     const int32_t *chain_prob;    // device int32[n_prob]: caller's pair index of every sorted pair (output slot)
     const int32_t *chain_units;   // device int32[n_units][2] = (first sorted pair, number of pairs)
+    long long *timing;            // diagnostic build of the fp4 kernel only (SLM_TC4_TIMING): per-phase cycle sums
 };
 
 }  // namespace tcp
