@@ -422,7 +422,9 @@ int slm_knn2_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_frames, int64
     // units first.  L keeps ~8 waves of clusters for balance while the cluster start-up is paid once per unit.
     std::vector<int32_t> sorted, prob, units;
     if (ctx->tc_chain_max > 1 && n_pairs >= 2 && n_pairs <= 32768) {
-        const int64_t m_tiles = (n_per_frame + 127) / 128, n_gpairs = (m_tiles + 7) / 8;
+        // query tiles per cluster: 2 x 8 on the fp4 kernel, 2 x 4 on the fp8 kernel
+        const bool fp4 = ctx->variant == SLM_VARIANT_TENSOR4 || (ctx->variant == SLM_VARIANT_AUTO && ctx->tc_fp4);
+        const int64_t m_tiles = (n_per_frame + 127) / 128, n_gpairs = fp4 ? (m_tiles + 15) / 16 : (m_tiles + 7) / 8;
         int64_t L = n_pairs * n_gpairs / ((int64_t)(ctx->sm_count / 2) * 8);
         L = std::max<int64_t>(std::max(1, ctx->tc_chain_min), std::min<int64_t>(L, ctx->tc_chain_max));
         if (L > 1) {

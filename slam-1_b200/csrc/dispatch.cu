@@ -25,10 +25,11 @@ int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_fram
     if (n_pairs > kMaxPairs) chain = nullptr;     // chain units index the whole (sorted) pair list
     for (int64_t p0 = 0; p0 < n_pairs; p0 += kMaxPairs) {
         int64_t n = n_pairs - p0 < kMaxPairs ? n_pairs - p0 : kMaxPairs;
-        if (ctx->variant == SLM_VARIANT_TENSOR ||
+        if (ctx->variant == SLM_VARIANT_TENSOR || ctx->variant == SLM_VARIANT_TENSOR4 ||
             (ctx->variant == SLM_VARIANT_AUTO && n_per_frame * n_per_frame >= kAutoTensorMinCmp))
             SLM_TRY(slm_tc_knn2_keys_batched(ctx, desc, n_per_frame, pairs_dev + 2 * p0, n,
-                                             keys_out + 2 * p0 * n_per_frame, stream, chain));
+                                             keys_out + 2 * p0 * n_per_frame, stream, chain,
+                                             ctx->variant == SLM_VARIANT_TENSOR4 || (ctx->variant == SLM_VARIANT_AUTO && ctx->tc_fp4)));
         else
             SLM_TRY(slm_popc_knn2_keys_batched(ctx, desc, n_per_frame, pairs_dev + 2 * p0, n,
                                                keys_out + 2 * p0 * n_per_frame, stream));

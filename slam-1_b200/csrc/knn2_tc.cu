@@ -1029,9 +1029,10 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     const int m_tiles = (p.nq + kTileM - 1) / kTileM;
     // CTA pairs (cta_group::2) need at least two query tiles to keep both halves of the M = 256 MMA busy
     const bool two_cta = m_tiles >= 2 && !ctx->force_1cta;
-    // fp4 (kind::mxf4, twice the fp8 rate) whenever CTA pairs apply; batches of frame-sized problems stay on the
-    // fp8 kernel (their chained instantiation and shared-memory refine are tuned for 16-row chunks)
-    const bool fp4 = two_cta && allow_fp4 && p.desc == nullptr;
+    // fp4 (kind::mxf4, twice the fp8 rate) whenever CTA pairs apply; batches of frame-sized problems only as chained
+    // batches (their fp4 instantiation walks the pairs of a query frame back to back and tracks 20-row chunks)
+    const bool chain_ok = chain && chain->n_units > 0 && chain->n_units < n_prob;
+    const bool fp4 = two_cta && allow_fp4 && (p.desc == nullptr || chain_ok);
     ctx->last_variant = fp4 ? SLM_VARIANT_TENSOR4 : SLM_VARIANT_TENSOR;
     p.tile_n = fp4 ? tc4::kTileN : kTileN;
     const int n_tiles = (p.nt + p.tile_n - 1) / p.tile_n;
@@ -1044,7 +1045,7 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         work_units = (p.n_groups + 1) / 2;
         // wide chunks keep the hot kernel's epilogue at 0.52 ALU ops per element; the refine pass re-scores two chunks per
         // query, so many-query problems take narrower ones
-        p.chunk = ctx->tc4_chunk > 0 ? ctx->tc4_chunk : (n_q <= 32768 ? 120 : 40);
+        p.chunk = p.desc != nullptr ? 20 : (ctx->tc4_chunk > 0 ? ctx->tc4_chunk : (n_q <= 32768 ? 120 : 40));
     } else if (two_cta) {
         // split the query tiles evenly over an even number of groups of at most kMaxMT2 tiles
         int n_groups = 2 * ((m_tiles + 2 * kMaxMT2 - 1) / (2 * kMaxMT2));
@@ -1125,8 +1126,14 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
     // Chained batch: short train frames (one cluster per query-group pair walks a whole frame in one epoch) whose
     // pairs share query frames -- grid.y runs over the units instead of the pairs.
     int grid_y = n_prob;
-    if (!fp4 && chain && two_cta && p.cpg == 1 && p.n_epochs == 1 && chain->n_units > 0 && chain->n_units < n_prob &&
-        n_tiles <= kMaxEpochTiles / 2) {
+    if (fp4 && p.desc != nullptr) {
+        // batched fp4 = chained fp4; a plan that needs several clusters or epochs per pair goes to the fp8 kernels
+        if (p.cpg != 1 || p.n_epochs != 1) return tc_run(ctx, p, n_prob, base, keys_out, stream, exchange, chain, false, phase_out);
+        p.chain_pairs = chain->pairs_sorted;
+        p.chain_prob = chain->prob;
+        p.chain_units = chain->units;
+        grid_y = chain->n_units;
+    } else if (!fp4 && chain_ok && two_cta && p.cpg == 1 && p.n_epochs == 1 && n_tiles <= kMaxEpochTiles / 2) {
         p.chunk = 16;      // the chained instantiation tracks 16-column candidate chunks
         p.chain_pairs = chain->pairs_sorted;
         p.chain_prob = chain->prob;
@@ -1220,11 +1227,11 @@ int slm_tc_knn2_exchange(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint
 }
 
 int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
-                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain)
+                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain, bool fp4)
 {
     TcParams p{};
     p.q = nullptr; p.t = nullptr; p.desc = desc; p.pairs = pairs_dev;
     p.frame_words = n_per_frame * 8;
     p.nq = (int)n_per_frame; p.nt = (int)n_per_frame;
-    return tc_run(ctx, p, (int)n_pairs, 0, keys_out, stream, nullptr, chain, false);
+    return tc_run(ctx, p, (int)n_pairs, 0, keys_out, stream, nullptr, chain, fp4);
 }

@@ -68,16 +68,21 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src
 }
 __device__ __forceinline__ void bar_sync_expanders() { asm volatile("bar.sync 1, %0;" ::"n"(kExpThreads) : "memory"); }
 
-// The tile sequence every role of a cluster walks: ranges unit, unit + cpg, ... , each of up to range_tiles tiles.
+// The tile sequence every role of a cluster walks: for every link of the unit (one link unless the batch is chained: the
+// train frames of the pairs that share this cluster's query frame), ranges unit, unit + cpg, ... of up to range_tiles tiles.
 struct TileIter {
-    int r, bt, n_bt;
+    int link, r, bt, n_bt;
+    int unit, n_links;
     bool done;
 };
-__device__ __forceinline__ void iter_start(TileIter &it, const TcParams &p, int unit, int total_tiles)
+__device__ __forceinline__ void iter_start(TileIter &it, const TcParams &p, int unit, int total_tiles, int n_links = 1)
 {
+    it.link = 0;
+    it.unit = unit;
+    it.n_links = n_links;
     it.r = unit;
     it.bt = 0;
-    it.done = unit >= p.n_ranges;
+    it.done = unit >= p.n_ranges || n_links <= 0;
     it.n_bt = it.done ? 0 : min(p.range_tiles, total_tiles - unit * p.range_tiles);
 }
 __device__ __forceinline__ void iter_next(TileIter &it, const TcParams &p, int total_tiles)
@@ -85,20 +90,12 @@ __device__ __forceinline__ void iter_next(TileIter &it, const TcParams &p, int t
     if (++it.bt == it.n_bt) {
         it.bt = 0;
         it.r += p.cpg;
-        if (it.r >= p.n_ranges) { it.done = true; return; }
+        if (it.r >= p.n_ranges) {
+            if (++it.link >= it.n_links) { it.done = true; return; }
+            it.r = it.unit;
+        }
         it.n_bt = min(p.range_tiles, total_tiles - it.r * p.range_tiles);
     }
-}
-
-// tcgen05.wait::ld that cannot be scheduled before `x` has been computed.  ptxas freely sinks the FMNMX reduction of piece
-// k below the (operand-less) wait for piece k + 1, which exposes the TMEM read latency again (first ncu source view of
-// this kernel: all stall samples sat on the wait right behind the LDTM).  Predicating the wait on the reduction's result
-// -- always true: every dot product is >= -256 -- makes the order a data dependency.
-__device__ __forceinline__ void tmem_wait_ld_after(float x)
-{
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "setp.gt.f32 p, %0, 0fF149F2CA;\n\t"          // x > -1e30
-                 "@p tcgen05.wait::ld.sync.aligned;\n\t}" ::"f"(x) : "memory");
 }
 
 // mbarrier wait of the hot loop: no spin counter, no printf path (the bounded tc::mbar_wait costs ~10 extra instructions and
@@ -134,10 +131,26 @@ __device__ __forceinline__ float max_cols(const uint32_t *v)
 
 // TIMING (diagnostic build of the same kernel, SLM_TC4_TIMING=1): two epilogue warps and the MMA warp of cluster 0 sum
 // clock64 intervals per phase and write them to p.timing -- where a job's 597 clk go.
-template <int CH, bool TIMING>
+// CHAIN (batches of frame-sized problems, config 3): grid.y indexes UNITS = runs of pairs that share the query frame; the
+// cluster expands that frame's query tiles once and walks the train frames of the run back to back, one candidate flush
+// per pair.  CH = 20 there: the refine pass re-scores two chunks per query and is the second-largest cost of such a batch.
+// maximum of 20 columns in 10 instructions (four chains of two FMNMX3, then FMNMX3 + FMNMX)
+__device__ __forceinline__ float max20(const uint32_t *v)
+{
+    auto f = [&](int i) { return __uint_as_float(v[i]); };
+    float m0 = fmaxf(fmaxf(f(0), f(4)), f(5)), m1 = fmaxf(fmaxf(f(1), f(6)), f(7));
+    float m2 = fmaxf(fmaxf(f(2), f(8)), f(9)), m3 = fmaxf(fmaxf(f(3), f(10)), f(11));
+    m0 = fmaxf(fmaxf(m0, f(12)), f(13));
+    m1 = fmaxf(fmaxf(m1, f(14)), f(15));
+    m2 = fmaxf(fmaxf(m2, f(16)), f(17));
+    m3 = fmaxf(fmaxf(m3, f(18)), f(19));
+    return fmaxf(fmaxf(fmaxf(m0, m1), m2), m3);
+}
+
+template <int CH, bool CHAIN, bool TIMING>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(TcParams p)
 {
-    static_assert(CH == 120 || CH == 40, "candidate chunk width");
+    static_assert(CH == 120 || CH == 40 || CH == 20, "candidate chunk width");
     constexpr int kCPT = tc4::kTileN / CH;             // chunks per tile: 2 or 6
     constexpr int kCPS = kCPT / 2;                     // chunks per epilogue set: 1 or 3
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -155,7 +168,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
     const int unit = item % p.cpg;                        // this cluster walks ranges unit, unit + cpg, ...
     const int group = gpair * 2 + (int)rank;              // may be == n_groups (idle half of an odd pair)
     const uint32_t *q = p.q;
-    const uint32_t *t = p.t;
+    int link_first = 0, n_links = 1;              // chained batch: sorted pairs [link_first, link_first + n_links)
+    if constexpr (CHAIN) {
+        const int2 cu = reinterpret_cast<const int2 *>(p.chain_units)[blockIdx.y];
+        link_first = cu.x;
+        n_links = cu.y;
+        q = p.desc + (long long)p.chain_pairs[2 * link_first] * p.frame_words;
+    }
+    // train rows / output slot of link l (the single problem when not chained)
+    auto link_train = [&](int l) -> const uint32_t * {
+        if constexpr (CHAIN) return p.desc + (long long)p.chain_pairs[2 * (link_first + l) + 1] * p.frame_words;
+        else return p.t;
+    };
+    auto link_prob = [&](int l) -> int {
+        if constexpr (CHAIN) return p.chain_prob[link_first + l];
+        else return (int)blockIdx.y;
+    };
 
     const int MT = p.mt;
     const int q_first = group * (MT * kTileM);
@@ -193,14 +221,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
         const int v = valid_rows(tile);
         if (v > 0) {
             mbar_arrive_expect_tx(&bars->raw_full[slot], (uint32_t)v * 32);
-            bulk_copy_g2s(sRaw_addr0 + (uint32_t)slot * kRawBytes, t + ((long long)tile * tc4::kTileN + (long long)rank * kHalf) * 8,
-                          (uint32_t)v * 32, &bars->raw_full[slot]);
+            bulk_copy_g2s(sRaw_addr0 + (uint32_t)slot * kRawBytes,
+                          link_train(pi_.link) + ((long long)tile * tc4::kTileN + (long long)rank * kHalf) * 8, (uint32_t)v * 32,
+                          &bars->raw_full[slot]);
         } else {
             tc::mbar_arrive(&bars->raw_full[slot]);
         }
     };
     TileIter pi;                                             // producer position: kRawStages tiles ahead of the expanders
-    iter_start(pi, p, unit, total_tiles);
+    iter_start(pi, p, unit, total_tiles, n_links);
     if (tid == kEpiThreads) {
         for (int s = 0; s < kRawStages && !pi.done; ++s) {
             produce(pi, s);
@@ -241,7 +270,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
         const int set = warp >> 2, quad = warp & 3;
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + set * kHalf;
         const int n_slots = p.cpg * p.n_epochs;
-        float2 *cand = p.cand + ((long long)blockIdx.y * p.nq) * n_slots * 2 + (long long)(unit * p.n_epochs) * 2 + set;
+        auto cand_of = [&](int link) {
+            return p.cand + ((long long)link_prob(link) * p.nq) * n_slots * 2 + (long long)(unit * p.n_epochs) * 2 + set;
+        };
+        float2 *cand = cand_of(0);
         float b1[kMaxMT4], b2[kMaxMT4];
 #pragma unroll
         for (int m = 0; m < kMaxMT4; ++m) { b1[m] = -FLT_MAX; b2[m] = -FLT_MAX; }
@@ -268,8 +300,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
         if constexpr (TIMING) tq = clock64();
         uint32_t X[40], Y[40], Z[40];        // three 40-column register buffers
         auto valid_cols_of = [&](const TileIter &ti) { return min(tc4::kTileN, p.nt - (ti.r * p.range_tiles + ti.bt) * tc4::kTileN); };
+        int cur_link = 0;
         TileIter it;
-        for (iter_start(it, p, unit, total_tiles); !it.done; iter_next(it, p, total_tiles), ++lt) {
+        for (iter_start(it, p, unit, total_tiles, n_links); !it.done; iter_next(it, p, total_tiles), ++lt) {
+            if (CHAIN && it.link != cur_link) {
+                // next pair of the chain: flush this pair's candidates, start over for the next output slot
+                for (; epoch < p.n_epochs; ++epoch) flush(epoch);
+                cur_link = it.link;
+                cand = cand_of(cur_link);
+                epoch = 0; lt = 0; j = 0; last_r = -1;
+            }
             if (it.r != last_r) {
                 if (last_r >= 0 && ++j % p.rpe == 0) { flush(epoch); ++epoch; lt = 0; }
                 last_r = it.r;
@@ -321,6 +361,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
                         const float mx2 = fmaxf(max_cols<32>(Z), max_cols<8>(Z + 32));
                         if constexpr (CH == 120) {
                             track(b1[m], b2[m], fmaf(fmaxf(fmaxf(mx0, mx1), mx2), kKeyScale, bias0));
+                        } else if constexpr (CH == 20) {
+                            // six 20-column chunks per warp and job: the halves of the three pieces
+                            track(b1[m], b2[m], fmaf(max20(X), kKeyScale, bias0));
+                            if (col0 + 20 < valid_cols) track(b1[m], b2[m], fmaf(max20(X + 20), kKeyScale, bias0 - 1.0f));
+                            if (col0 + 40 < valid_cols) track(b1[m], b2[m], fmaf(max20(Y), kKeyScale, bias0 - 2.0f));
+                            if (col0 + 60 < valid_cols) track(b1[m], b2[m], fmaf(max20(Y + 20), kKeyScale, bias0 - 3.0f));
+                            if (col0 + 80 < valid_cols) track(b1[m], b2[m], fmaf(max20(Z), kKeyScale, bias0 - 4.0f));
+                            if (col0 + 100 < valid_cols) track(b1[m], b2[m], fmaf(max20(Z + 20), kKeyScale, bias0 - 5.0f));
                         } else {
                             track(b1[m], b2[m], fmaf(mx0, kKeyScale, bias0));
                             if (col0 + 40 < valid_cols) track(b1[m], b2[m], fmaf(mx1, kKeyScale, bias0 - 1.0f));
@@ -365,7 +413,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
         const bool two_rows = et < kHalf - kExpThreads;          // threads 0..23 also expand row 96 + et
         int sb = 0, phb = 0, sr = 0, phr = 0;
         TileIter it;
-        for (iter_start(it, p, unit, total_tiles); !it.done; iter_next(it, p, total_tiles)) {
+        for (iter_start(it, p, unit, total_tiles, n_links); !it.done; iter_next(it, p, total_tiles)) {
             const int tile = it.r * p.range_tiles + it.bt;
             const int v = valid_rows(tile);
             tc::mbar_wait(&bars->raw_full[sr], phr, 50 + sr);
@@ -407,7 +455,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
             long long tq = 0;
             if constexpr (TIMING) tq = clock64();
             TileIter it;
-            for (iter_start(it, p, unit, total_tiles); !it.done; iter_next(it, p, total_tiles)) {
+            for (iter_start(it, p, unit, total_tiles, n_links); !it.done; iter_next(it, p, total_tiles)) {
                 tc::mbar_wait_cluster(&bars->b_full[s], ph, 31 + s);
                 tc::tc_fence_after();
                 if constexpr (TIMING) { const long long c = clock64(); tm[0] += c - tq; tq = c; }
@@ -441,7 +489,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) knn2_t
     if (warp == mma_warp) tc::tmem_dealloc_2cta(tmem, 512);
 }
 
-template <int CH, bool TIMING>
+template <int CH, bool CHAIN, bool TIMING>
 int launch_tc4(const TcParams &p, int grid_y, cudaStream_t stream)
 {
     const size_t smem_max = (size_t)kMaxMT4 * tc4::kATileBytes + kBStages * tc4::kBHalfBytes + kRawStages * kRawBytes + sizeof(Bars4) + 64;
@@ -449,13 +497,13 @@ int launch_tc4(const TcParams &p, int grid_y, cudaStream_t stream)
     int dev = 0;
     SLM_CUDA(cudaGetDevice(&dev));
     if (!configured[dev & 63].load(std::memory_order_acquire)) {
-        SLM_CUDA(cudaFuncSetAttribute(knn2_tc4_kernel<CH, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        SLM_CUDA(cudaFuncSetAttribute(knn2_tc4_kernel<CH, CHAIN, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         configured[dev & 63].store(true, std::memory_order_release);
     }
     const size_t smem = (size_t)p.mt * tc4::kATileBytes + kBStages * tc4::kBHalfBytes + kRawStages * kRawBytes + sizeof(Bars4) + 64;
     const int n_gpairs = (p.n_groups + 1) / 2;
     dim3 grid((unsigned)(2 * n_gpairs * p.cpg), (unsigned)grid_y);
-    knn2_tc4_kernel<CH, TIMING><<<grid, kThreads4, smem, stream>>>(p);
+    knn2_tc4_kernel<CH, CHAIN, TIMING><<<grid, kThreads4, smem, stream>>>(p);
     SLM_CUDA(cudaGetLastError());
     return SLM_OK;
 }
@@ -466,13 +514,13 @@ int slm_tc4_launch(slm_ctx *ctx, const tcp::TcParams &p_in, int grid_y, cudaStre
 {
     tcp::TcParams p = p_in;
     if (p.mt < 1 || p.mt > kMaxMT4) return slm_fail(SLM_ERR_INVALID, "tc4: %d query tiles per CTA", p.mt);
-    if (ctx->tc4_timing && p.chunk == 120) {
+    if (ctx->tc4_timing && p.chunk == 120 && !p.chain_pairs) {
         // diagnostic: per-phase cycle sums of cluster 0 (synchronous; SLM_TC4_TIMING=1)
         long long *dev = nullptr, h[24] = {};
         SLM_CUDA(cudaMalloc(&dev, sizeof(h)));
         SLM_CUDA(cudaMemset(dev, 0, sizeof(h)));
         p.timing = dev;
-        SLM_TRY((launch_tc4<120, true>(p, grid_y, stream)));
+        SLM_TRY((launch_tc4<120, false, true>(p, grid_y, stream)));
         SLM_CUDA(cudaStreamSynchronize(stream));
         SLM_CUDA(cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost));
         SLM_CUDA(cudaFree(dev));
@@ -487,9 +535,13 @@ int slm_tc4_launch(slm_ctx *ctx, const tcp::TcParams &p_in, int grid_y, cudaStre
                 h[16] / n, h[17] / n, h[18] / n, (h[16] + h[17] + h[18]) / n);
         return SLM_OK;
     }
+    if (p.chain_pairs) {
+        if (p.chunk != 20) return slm_fail(SLM_ERR_INVALID, "tc4: chained batches track 20-row chunks (got %d)", p.chunk);
+        return launch_tc4<20, true, false>(p, grid_y, stream);
+    }
     switch (p.chunk) {
-    case 120: return launch_tc4<120, false>(p, grid_y, stream);
-    case 40: return launch_tc4<40, false>(p, grid_y, stream);
+    case 120: return launch_tc4<120, false, false>(p, grid_y, stream);
+    case 40: return launch_tc4<40, false, false>(p, grid_y, stream);
     default: return slm_fail(SLM_ERR_INVALID, "tc4: unsupported candidate chunk width %d", p.chunk);
     }
 }

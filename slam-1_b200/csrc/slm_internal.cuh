@@ -217,7 +217,8 @@ struct slm_chain {
     int n_units;
 };
 int slm_tc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
-                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain = nullptr);
+                             int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain = nullptr,
+                             bool fp4 = false);
 
 // ---- variant B: b1 AND.POPC mma.sync tiles (knn2_bmma.cu; emulated by ptxas on sm_100a) -----------
 int slm_bmma_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,

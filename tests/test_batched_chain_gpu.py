@@ -39,11 +39,18 @@ def _batched(ctx, desc, pairs, ratio=(7, 10)):
     return idx.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy()
 
 
-@pytest.mark.parametrize("n", [129, 300, 777, 1100])
+# "tensor" = fp8 kernel (16-row chunks), "tensor4" = mxf4 kernel (240-row tiles, 20-row chunks): both have a chained instantiation
+VARIANTS = ["tensor", "tensor4"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n", [129, 300, 777, 1100, 2000])
 @pytest.mark.parametrize("chain_min", [2, 3, 8])
-def test_chained_batches_equal_oracle_pair_by_pair(n, chain_min):
-    ctx = _ctx(SLM_TC_CHAIN_MIN=chain_min)
-    ctx.set_variant("tensor")
+def test_chained_batches_equal_oracle_pair_by_pair(n, chain_min, variant):
+    if n == 2000 and chain_min != 3:
+        pytest.skip("the config-3 frame size once per variant")
+    ctx = _ctx(SLM_TC_CHAIN_MIN=chain_min, SLM_TC_MAX_CPG=1)      # one cluster per unit: the chained instantiation is taken
+    ctx.set_variant(variant)
     frames = 7
     rng = np.random.default_rng(n + chain_min)
     base = synth.heavy_ties(n, 60 + n) if n == 129 else synth.uniform(n, 50 + n)
@@ -57,11 +64,13 @@ def test_chained_batches_equal_oracle_pair_by_pair(n, chain_min):
         oi, od = orc.c_knn2(desc[a], desc[b])
         assert np.array_equal(idx[p], oi) and np.array_equal(dist[p], od), (n, chain_min, p, a, b)
         assert np.array_equal(acc[p], orc.c_ratio(od, 7, 10)), (n, chain_min, p)
+    assert ctx.last_kernel() == ("knn2_tc4_kernel" if variant == "tensor4" else "knn2_tc2_kernel")
     ctx.close()
 
 
-def test_chain_plan_is_invisible_in_the_results():
-    """Same batch with chaining off and on: byte-identical outputs."""
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_chain_plan_is_invisible_in_the_results(variant):
+    """Same batch with chaining off and on: byte-identical outputs (without a chain plan the batch runs on the fp8 kernel)."""
     frames, n = 9, 520
     rng = np.random.default_rng(3)
     desc = np.stack([synth.uniform(n, 900 + f) for f in range(frames)])
@@ -69,7 +78,7 @@ def test_chain_plan_is_invisible_in_the_results():
     pairs = np.array([(i, j) for i in range(frames) for j in range(frames) if i != j], dtype=np.int32)
     off, on = _ctx(SLM_TC_CHAIN=0), _ctx(SLM_TC_CHAIN_MIN=5)
     for c in (off, on):
-        c.set_variant("tensor")
+        c.set_variant(variant)
     a, b = _batched(off, desc, pairs), _batched(on, desc, pairs)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
@@ -78,8 +87,9 @@ def test_chain_plan_is_invisible_in_the_results():
     on.close()
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("n", [260, 1000])
-def test_frame_refine_kernel_many_pairs(n):
+def test_frame_refine_kernel_many_pairs(n, variant):
     """>= 148 pairs switch the refine step to one CTA per pair with the train frame in shared memory; with and
     without chaining, against the oracle and against the L2-fed refine kernel."""
     frames = 18
@@ -92,7 +102,7 @@ def test_frame_refine_kernel_many_pairs(n):
     ref = None
     for env in (dict(SLM_TC_CHAIN_MIN=4), dict(SLM_TC_CHAIN=0), dict(SLM_TC_NO_FRAME_REFINE=1, SLM_TC_CHAIN=0)):
         ctx = _ctx(**env)
-        ctx.set_variant("tensor")
+        ctx.set_variant(variant)
         out = _batched(ctx, desc, pairs)
         ctx.close()
         if ref is None:
