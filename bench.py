@@ -40,6 +40,9 @@ WORKLOADS = {
                nq=2000, nt=10_000_000, ratio=(7, 10), cross=False, sharded=True),
     "c4": dict(name="c4 BoW word assignment: 1M descriptors x 64k-word binary vocabulary, vocab row-sharded",
                nq=1_000_000, nt=65536, ratio=None, cross=False, sharded=True),
+    # the same job cut the other way (note): vocabulary replicated, query slices, no candidate exchange
+    "c4q": dict(name="c4 BoW word assignment, QUERY-sharded alternative: 1M descriptors sliced over the ranks, 64k-word vocabulary replicated",
+                nq=1_000_000, nt=65536, ratio=None, cross=False, sharded=True, shard_by="queries"),
     "c3": dict(name="c3 local-mapping batch: 64 keyframes x 2000 descriptors, 2016 unordered pairs, ratio 0.7",
                nq=2000, nt=2000, frames=64, ratio=(7, 10), cross=False, sharded=False),
     "c2": dict(name="c2 tracking vs local map: 2000 x 20000, kNN-2 + cross-check", nq=2000, nt=20000,
@@ -271,7 +274,7 @@ def measure(args, wl_id, env, headline):
     import torch.distributed as dist
     import slammatch
     from slammatch import _lib
-    from slammatch.sharded import ShardedMatcher, shard_bounds
+    from slammatch.sharded import QueryShardedMatcher, ShardedMatcher, shard_bounds
 
     rank, world, local, dev, ctx, peaks = env["rank"], env["world"], env["local"], env["dev"], env["ctx"], env["peaks"]
     w = WORKLOADS[wl_id]
@@ -279,12 +282,13 @@ def measure(args, wl_id, env, headline):
     steps = args.steps if headline else max(3, min(args.steps, args.config_steps))
     e2e_steps = max(1, min(steps, args.e2e_steps if headline else 2))
     sharded = w["sharded"] and world > 1
+    by_q = sharded and w.get("shard_by") == "queries"
     nq, nt = w["nq"], w["nt"]
     num, den = w["ratio"] if w["ratio"] else (0, 1)
     ctx.set_variant(args.variant)
 
     # ---- inputs (host, pinned) and device-resident copies ----------------------------------------
-    first, last = shard_bounds(nt, world)[rank] if sharded else (0, nt)
+    first, last = shard_bounds(nt, world)[rank] if (sharded and not by_q) else (0, nt)
     extra = None
     if wl_id == "c3":
         frames = w["frames"]
@@ -311,8 +315,9 @@ def measure(args, wl_id, env, headline):
         q_d = q_pin.to(dev)
         t_d = t_pin.to(dev)
         cmp_per_step = float(nq) * nt            # whole job, all ranks together
-        in_bytes = q_h.nbytes + t_h.nbytes
-        sm = ShardedMatcher(t_d, first, ratio=w["ratio"], variant=args.variant, exchange=args.exchange, total_rows=nt)
+        in_bytes = (q_h.nbytes // world if by_q else q_h.nbytes) + t_h.nbytes      # what THIS rank uploads per e2e step
+        sm = (QueryShardedMatcher(t_d, ratio=w["ratio"], variant=args.variant) if by_q else
+              ShardedMatcher(t_d, first, ratio=w["ratio"], variant=args.variant, exchange=args.exchange, total_rows=nt))
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def step_device():
@@ -410,7 +415,7 @@ def measure(args, wl_id, env, headline):
     if not args.no_parity:
         n_sel = torch.zeros(1, dtype=torch.int64, device=dev)
         if rank == 0:
-            t_full = t_h if (wl_id == "c3" or not sharded) else train_rows(cfg_id, 0, nt)
+            t_full = t_h if (wl_id == "c3" or not sharded or by_q) else train_rows(cfg_id, 0, nt)
             sel, e_i, e_d, e_a = parity_expected(wl_id, w, cfg_id, q_h, t_full, extra)
             del t_full
             n_sel[0] = sel.shape[0]
@@ -466,6 +471,7 @@ def measure(args, wl_id, env, headline):
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
            "steps": e2e_steps,
            "api": ("slammatch.knn2(pinned host arrays) -> slm_knn2_host" if not (sharded or wl_id == "c3") else
+                   "QueryShardedMatcher.knn2_host(host query slice, host train set)" if by_q else
                    "ShardedMatcher.knn2_host(host queries, host shard)" if sharded else
                    "pinned host -> device copy + slm_knn2_batched + result read-back")}
     if world == 1 and wl_id != "c3":
@@ -557,7 +563,8 @@ def measure(args, wl_id, env, headline):
         "ms_min": float(np.min(per_step)), "ms_median": float(np.median(per_step)),
         "variant": variant, "nq": nq, "nt": nt,
         "l2": "inputs larger than L2 (streamed from HBM every step)" if flush is None else "256 MiB L2 flush between timed steps",
-        "parallelism": (f"train rows sharded over {world} ranks, exchange of packed top-2 keys ({sm.last_exchange}) + merge"
+        "parallelism": (f"queries sliced over {world} ranks, train set replicated, {sm.last_exchange}" if by_q else
+                        f"train rows sharded over {world} ranks, exchange of packed top-2 keys ({sm.last_exchange}) + merge"
                         if sharded else ("single GPU" if world == 1 else f"{world} replicas")),
         "scaling": "strong" if w["sharded"] else "replicas",
         "matched_per_step": matched, "matched_queries_per_s": matched * jobs / (dev_ms / steps * 1e-3),
@@ -600,7 +607,7 @@ def ours(args):
     # every other BASELINE config rides in the same line: all of them on one GPU, the sharded ones (c4) under torchrun
     if args.configs == "auto":
         others = [c for c in ("c4", "c3", "c2", "c1", "h1") if c != args.workload] if world == 1 else \
-                 [c for c in ("c4", "c5") if c != args.workload]
+                 [c for c in ("c4", "c4q", "c5") if c != args.workload]
     elif args.configs == "none":
         others = []
     else:

@@ -88,13 +88,17 @@ __device__ __forceinline__ bool slm_exchange_wait_flags(const slm_exchange &ex, 
 
 // Called by ALL threads of EVERY block of the producer kernel after their stores: the block that finishes last
 // publishes `step` into this rank's flag on every peer.
-// `wrote` = this thread issued peer stores (only those threads need the system-scope fence).
+// `wrote` is kept for the callers' bookkeeping only.
 __device__ __forceinline__ void slm_exchange_publish(const slm_exchange &ex, bool wrote = true, int phase = 0)
 {
     __shared__ bool s_last;
-    if (wrote) __threadfence_system();
+    (void)wrote;
+    // ONE system-scope fence per block, by the thread that counts the block in: the barrier orders every thread's peer
+    // stores before it and the fence is cumulative (the pattern of a grid-wide barrier).  A fence per storing thread was a
+    // third of the refine kernel on config 4 (a million MEMBAR.SYS).
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         s_last = atomicAdd(ex.done_counter, 1u) == gridDim.x - 1;
         if (s_last) *ex.done_counter = 0;
     }

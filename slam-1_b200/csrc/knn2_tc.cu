@@ -587,23 +587,50 @@ __device__ __forceinline__ void top2_insert_max(unsigned long long &k1, unsigned
 // Candidate key -> (dot + 257) << 32 | ~global chunk, so that a 64-bit max prefers the larger dot and, on ties,
 // the chunk with the lower global index.  Undoes the unit's strided range walk: the key carries the chunk counter
 // inside the unit's candidate epoch.
+// x / d and x % d for 0 <= x < 2^17, d >= 1 through a float reciprocal: (x + 0.5) / d stays at least 0.5 / d away from every
+// integer while the float error is below 2^-5 / d, so the truncation is exact -- ~8 instructions instead of ~25 per integer
+// division (this function runs for every candidate of every query: 296 per query on config 5).
+__device__ __forceinline__ void small_divmod(int x, int d, int &q, int &r)
+{
+    q = __float2int_rz(((float)x + 0.5f) * __frcp_rn((float)d));
+    r = x - q * d;
+}
 __device__ __forceinline__ unsigned long long cand_to_chunk_key(const TcParams &p, float key, int slot)
 {
     const int ki = (int)key + kKeyBias;
     const int lc = kChunkMask - (ki & kChunkMask);
-    const int unit = slot / p.n_epochs, epoch = slot % p.n_epochs;
-    const int cpt = p.tile_n / p.chunk;                       // chunks per tile
-    const int lt = lc / cpt;                                  // tile counter inside the epoch
-    const int range = unit + (epoch * p.rpe + lt / p.range_tiles) * p.cpg;
-    const unsigned gchunk = (unsigned)((range * p.range_tiles + lt % p.range_tiles) * cpt + lc % cpt);
+    int unit = slot, epoch = 0, lt, lcr, rq, rr;
+    if (p.n_epochs > 1) small_divmod(slot, p.n_epochs, unit, epoch);
+    small_divmod(lc, p.tile_n / p.chunk, lt, lcr);            // tile counter inside the epoch, chunk inside the tile
+    small_divmod(lt, p.range_tiles, rq, rr);
+    const int range = unit + (epoch * p.rpe + rq) * p.cpg;
+    const unsigned gchunk = (unsigned)((range * p.range_tiles + rr) * (p.tile_n / p.chunk) + lcr);
     return ((unsigned long long)((ki >> kChunkBits) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk);
 }
+// The same for a plan with one unit and one epoch per group (cpg * n_epochs == 1): the chunk counter is the global chunk --
+// none of the five integer divisions above, which were half of the refine kernel's instructions on config 4.
+__device__ __forceinline__ unsigned long long cand_to_chunk_key_1(float key)
+{
+    const int ki = (int)key + kKeyBias;
+    return ((unsigned long long)((ki >> kChunkBits) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(kChunkMask - (ki & kChunkMask)));
+}
 
-// Exact distance of one row pair (XOR + POPC), the arithmetic of the reference's matcher.
+// Exact distance of one row pair, the arithmetic of the reference's matcher (XOR + POPC over 256 bits) -- with three
+// carry-save adders in front of the POPCs: POPC is a quarter-rate (XU) instruction and eight per row bounded the refine
+// kernels (XU 64 clk per warp and row against 36 on the ALU pipe).  csa(a, b, c) = (a ^ b ^ c, maj(a, b, c)) is two LOP3;
+// 8 words -> 2 words of weight 1 + 3 of weight 2 = 5 POPC + 6 extra LOP3, which balances the two pipes at ~40 clk.
+__device__ __forceinline__ void csa(unsigned a, unsigned b, unsigned c, unsigned &sum, unsigned &carry)
+{
+    sum = a ^ b ^ c;
+    carry = (a & b) | (a & c) | (b & c);
+}
 __device__ __forceinline__ unsigned hamming256(const uint4 &qa, const uint4 &qb, const uint4 &ta, const uint4 &tb)
 {
-    return __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
-           __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+    unsigned s1, c1, s2, c2, s3, c3;
+    csa(qa.x ^ ta.x, qa.y ^ ta.y, qa.z ^ ta.z, s1, c1);
+    csa(qa.w ^ ta.w, qb.x ^ tb.x, qb.y ^ tb.y, s2, c2);
+    csa(s1, s2, qb.z ^ tb.z, s3, c3);
+    return __popc(s3) + __popc(qb.w ^ tb.w) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
 }
 
 // Exact key of a candidate row inside the two winning chunks: (distance << 8) | (chunk selector << 7) | position, so a
@@ -615,6 +642,42 @@ __device__ __forceinline__ unsigned long long refine_widen(unsigned k, unsigned 
     if (k == 0xFFFFFFFFu) return kKeyNone;
     const long long row = (long long)((k & 128u) ? ghi : glo) * chunk + (k & 127u);
     return ((unsigned long long)(k >> 8) << 32) | (unsigned long long)(base + row);
+}
+
+// Exact top-2 of the rows of the two winning chunks (glo < ghi; 0xFFFFFFFF = no such chunk) of a train set in global
+// memory, for the G lanes of one query: the 2 x chunk positions as ONE run over the lanes, U rows per lane in flight (the rows
+// come from L2 / HBM), branch-free -- a position outside the run or the train set, or of a chunk that does not exist
+// (row < 0), reads a clamped row and its key is replaced by "none".
+template <int G, int U>
+__device__ __forceinline__ void refine_rows(const uint32_t *t, int nt, int chunk, unsigned glo, unsigned ghi, int sub,
+                                            const uint4 &qa, const uint4 &qb, unsigned &k1, unsigned &k2)
+{
+    const uint4 *t4 = reinterpret_cast<const uint4 *>(t);
+    const int lo0 = (int)glo * chunk, hi0 = (int)ghi * chunk - chunk, n_pos = 2 * chunk;
+    const unsigned last = (unsigned)max(nt, 1) - 1u;
+    for (int e0 = sub; e0 < n_pos; e0 += U * G) {
+        uint4 ta[U], tb[U];
+        unsigned row[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * G;
+            const unsigned r = (unsigned)((e >= chunk ? hi0 : lo0) + e);
+            row[u] = e < n_pos ? r : 0xFFFFFFFFu;
+            const uint4 *ts = t4 + 2ull * min(r, last);
+            ta[u] = __ldg(ts);
+            tb[u] = __ldg(ts + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * G;
+            const unsigned code = (unsigned)e + (e >= chunk ? 128u - (unsigned)chunk : 0u);   // (selector << 7) | position
+            unsigned key = (hamming256(qa, qb, ta[u], tb[u]) << 8) | code;
+            key = row[u] < (unsigned)nt ? key : 0xFFFFFFFFu;
+            const unsigned m = max(k1, key);
+            k1 = min(k1, key);
+            k2 = min(k2, m);
+        }
+    }
 }
 
 // G lanes per (problem, query); 32 / G queries per warp.
@@ -645,8 +708,8 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
     const long long gq = q_block + (long long)it * kQPB + (threadIdx.x >> 5) * kQPW + lane / G;
     const bool live = gq < n_q;
     const long long gqc = live ? gq : 0;
-    const int prob = (int)(gqc / p.nq);
-    const int qi = (int)(gqc % p.nq);
+    const int prob = p.n_prob == 1 ? 0 : (int)(gqc / p.nq);          // (a 64-bit division is ~100 instructions)
+    const int qi = p.n_prob == 1 ? (int)gqc : (int)(gqc - (long long)prob * p.nq);
     const uint32_t *q = p.q;
     const uint32_t *t = p.t;
     if (p.desc != nullptr) {
@@ -665,7 +728,15 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
         const float key = cand[ci];
         if (key > -1.0e30f) top2_insert_max(c1, c2, cand_to_chunk_key(p, key, ci >> 2));
     };
-    if (n_cand <= 8) {
+    if (n_cand == 4) {
+        // one unit, one epoch (the usual plan): the four packed keys are directly comparable (larger = larger dot, then lower
+        // chunk) and name four different chunks -- a top-2 of four floats, and only the two winners are converted
+        const float4 c4 = *reinterpret_cast<const float4 *>(cand);
+        const float ca = fmaxf(c4.x, c4.y), cb = fminf(c4.x, c4.y), cc = fmaxf(c4.z, c4.w), cd = fminf(c4.z, c4.w);
+        const float f1 = fmaxf(ca, cc), f2 = fmaxf(fminf(ca, cc), fmaxf(cb, cd));
+        c1 = f1 > -1.0e30f ? cand_to_chunk_key_1(f1) : 0ull;
+        c2 = f2 > -1.0e30f ? cand_to_chunk_key_1(f2) : 0ull;
+    } else if (n_cand <= 8) {
         for (int ci = 0; ci < n_cand; ++ci) consider(ci);          // every lane of the group scans all: no shuffles
     } else {
 #pragma unroll 4
@@ -683,34 +754,9 @@ __global__ void __launch_bounds__(256) tc_refine_kernel(TcParams p, long long ba
     unsigned gb = c2 ? 0xFFFFFFFFu - (unsigned)(c2 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
     const unsigned glo = min(ga, gb), ghi = max(ga, gb);           // 0xFFFFFFFF = no such chunk
     unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const unsigned g = s == 0 ? glo : ghi;
-        if (g == 0xFFFFFFFFu) continue;
-        // four rows per lane in flight: the candidate rows come from HBM / L2 and every trip of a rolled loop would expose
-        // the full load latency (this loop was most of the refine kernel's 10 us on config 5)
-        for (int pos0 = sub; pos0 < p.chunk; pos0 += 4 * G) {
-            uint4 ta[4], tb[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int pos = pos0 + u * G;
-                const long long row = min((long long)g * p.chunk + pos, (long long)p.nt - 1);
-                const uint4 *ts = reinterpret_cast<const uint4 *>(t + row * 8);
-                ta[u] = __ldg(ts);
-                tb[u] = __ldg(ts + 1);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int pos = pos0 + u * G;
-                if (pos < p.chunk && (long long)g * p.chunk + pos < p.nt) {
-                    const unsigned key = refine_key(hamming256(qa, qb, ta[u], tb[u]), s, pos);
-                    const unsigned m = max(k1, key);
-                    k1 = min(k1, key);
-                    k2 = min(k2, m);
-                }
-            }
-        }
-    }
+    // 2 x chunk / G positions per lane: 30 / 10 / 5 (chunks of 120 / 40 / 20 rows) in batches of five, 8 / 4 (32 / 16) of four
+    if ((2 * p.chunk / G) % 5 == 0) refine_rows<G, 5>(t, p.nt, p.chunk, glo, ghi, sub, qa, qb, k1, k2);
+    else refine_rows<G, 4>(t, p.nt, p.chunk, glo, ghi, sub, qa, qb, k1, k2);
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
         const unsigned o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o);
@@ -769,7 +815,13 @@ __global__ void __launch_bounds__(256) tc_chunk_keys_kernel(TcParams p, long lon
             const float key = cand[ci];
             if (key > -1.0e30f) top2_insert_max(c1, c2, cand_to_chunk_key(p, key, ci >> 2));
         };
-        if (n_cand <= 8) {
+        if (n_cand == 4) {                          // as in tc_refine_kernel
+            const float4 c4 = *reinterpret_cast<const float4 *>(cand);
+            const float ca = fmaxf(c4.x, c4.y), cb = fminf(c4.x, c4.y), cc = fmaxf(c4.z, c4.w), cd = fminf(c4.z, c4.w);
+            const float f1 = fmaxf(ca, cc), f2 = fmaxf(fminf(ca, cc), fmaxf(cb, cd));
+            c1 = f1 > -1.0e30f ? cand_to_chunk_key_1(f1) : 0ull;
+            c2 = f2 > -1.0e30f ? cand_to_chunk_key_1(f2) : 0ull;
+        } else if (n_cand <= 8) {
             for (int ci = 0; ci < n_cand; ++ci) consider(ci);
         } else {
             for (int ci = sub; ci < n_cand; ci += G) consider(ci);
@@ -913,37 +965,33 @@ __global__ void __launch_bounds__(kRefineFrameThreads) tc_refine_frame_kernel(Tc
         const bool live = qi < p.nq;
         const int qc = live ? qi : 0;
         // ---- phase 1: the best two chunks out of the four candidates (two epilogue sets x best / second) ----
+        // one unit, one epoch: the chunk counter in a key IS the global chunk, so the packed keys of all four candidates are
+        // directly comparable (larger = larger dot, then lower chunk) and the two sets cover disjoint chunks: a top-2 of four
+        // floats (7 FMNMX) instead of four 64-bit insertions (a quarter of this kernel's issue slots)
         const float4 c4 = __ldg(cand4 + qc);
-        const float cf[4] = {c4.x, c4.y, c4.z, c4.w};
-        unsigned long long c1 = 0, c2 = 0;
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-            if (cf[ci] > -1.0e30f) {
-                const int ki = (int)cf[ci] + kKeyBias;
-                const unsigned gchunk = (unsigned)(kChunkMask - (ki & kChunkMask));   // one unit, one epoch: chunk counter = global chunk
-                top2_insert_max(c1, c2, ((unsigned long long)((ki >> kChunkBits) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gchunk));
-            }
-        }
-        const unsigned ga = c1 ? 0xFFFFFFFFu - (unsigned)(c1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
-        const unsigned gb = c2 ? 0xFFFFFFFFu - (unsigned)(c2 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+        const float ca = fmaxf(c4.x, c4.y), cb = fminf(c4.x, c4.y), cc = fmaxf(c4.z, c4.w), cd = fminf(c4.z, c4.w);
+        const float f1 = fmaxf(ca, cc), f2 = fmaxf(fminf(ca, cc), fmaxf(cb, cd));
+        const unsigned ga = f1 > -1.0e30f ? (unsigned)(kChunkMask - (((int)f1 + kKeyBias) & kChunkMask)) : 0xFFFFFFFFu;
+        const unsigned gb = f2 > -1.0e30f ? (unsigned)(kChunkMask - (((int)f2 + kKeyBias) & kChunkMask)) : 0xFFFFFFFFu;
         const unsigned glo = min(ga, gb), ghi = max(ga, gb);
         // ---- phase 2: exact re-scoring of those rows from shared memory ----
         const uint4 *qs = reinterpret_cast<const uint4 *>(q + (long long)qc * 8);
         const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
         unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const unsigned g = s == 0 ? glo : ghi;
-            if (g == 0xFFFFFFFFu) continue;
-            for (int pos = sub; pos < p.chunk; pos += G) {
-                const int row = (int)g * p.chunk + pos;
-                if (row < p.nt) {
-                    const unsigned key = refine_key(hamming256(qa, qb, s_rows[row], s_rows[p.nt + row]), s, pos);
-                    const unsigned m = max(k1, key);
-                    k1 = min(k1, key);
-                    k2 = min(k2, m);
-                }
-            }
+        // the rows of both chunks as ONE run of 2 x chunk positions over the 8 lanes (20-row chunks: 5 trips, not 2 x 3),
+        // branch-free: a position outside the frame (or of a chunk that does not exist: row < 0) reads a clamped row and
+        // its key is replaced by "none" -- a branch per row cost a third of the loop's issue slots
+        const int lo0 = (int)glo * p.chunk, hi0 = (int)ghi * p.chunk - p.chunk;
+        for (int e = sub; e < 2 * p.chunk; e += G) {
+            const bool s = e >= p.chunk;
+            const unsigned row = (unsigned)((s ? hi0 : lo0) + e);
+            const unsigned rc = min(row, (unsigned)p.nt - 1u);
+            const unsigned code = (unsigned)e + (s ? 128u - (unsigned)p.chunk : 0u);       // (selector << 7) | position
+            unsigned key = (hamming256(qa, qb, s_rows[rc], s_rows[p.nt + rc]) << 8) | code;
+            key = row < (unsigned)p.nt ? key : 0xFFFFFFFFu;
+            const unsigned m = max(k1, key);
+            k1 = min(k1, key);
+            k2 = min(k2, m);
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {

@@ -313,3 +313,103 @@ class ShardedMatcher:
         h = packed.cpu().numpy()
         return (h[:, 0:8].copy().view(np.int32).reshape(nq, 2), h[:, 8:16].copy().view(np.int32).reshape(nq, 2),
                 h[:, 16].copy())
+
+
+class QueryShardedMatcher:
+    """The other decomposition of a multi-GPU search (note): the train set is REPLICATED and the
+    QUERIES are split into contiguous slices, one per rank.
+
+    It fits a small train set searched by very many queries -- BASELINE config 4: one million descriptors against a 2 MB
+    vocabulary -- where the train-sharded form repeats the per-query work (candidate re-scoring, key exchange, merge) on
+    every rank.  Here a rank runs the plain single-GPU search (slm_knn2_filter) on its slice, writing straight into its
+    part of the result arrays, and the only communication is the in-place all-gather of the finished results (17 bytes per
+    query): no candidate exchange, no merge, and the result is trivially identical to the single-GPU one.  It does not
+    apply when the train set is what is too large for one GPU (config 5) -- that is what ShardedMatcher is for.
+
+    ``knn2_slice(q_slice, out_idx, out_dist, out_acc)`` defaults to the CUDA entry point; tests inject a CPU stand-in to
+    exercise the plumbing under gloo.
+    """
+
+    def __init__(self, train, group=None, ratio=(7, 10), cross_check: bool = False, variant: Optional[str] = None,
+                 knn2_slice: Optional[Callable] = None):
+        import torch.distributed as dist
+        self.train = train
+        self.group = group
+        self.ratio = ratio
+        self.cross_check = bool(cross_check)
+        self._variant = variant
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self._knn2_slice = knn2_slice or self._cuda_knn2_slice
+        self._bufs = None
+        self.last_exchange = "none"
+
+    def _cuda_knn2_slice(self, q, idx, dist_, acc):
+        import torch
+        from . import _lib
+        ctx = _lib.context(self.train.device.index or 0)
+        nq, nt = q.shape[0], self.train.shape[0]
+        if nq == 0:
+            return
+        num, den = self.ratio if self.ratio is not None else (0, 1)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        with ctx.using(self._variant):
+            _lib.check(ctx.lib.slm_knn2_filter(ctx.handle, q.data_ptr(), nq, self.train.data_ptr() if nt else None, nt, 0,
+                                               int(num), int(den), int(self.cross_check), idx.data_ptr(), dist_.data_ptr(),
+                                               acc.data_ptr(), stream))
+
+    def slice_bounds(self, nq: int):
+        """(rows per rank, first, last_exclusive) of this rank's query slice: equal slices, the last ones ragged or empty."""
+        per = -(-nq // self.world) if nq else 0
+        lo = min(nq, self.rank * per)
+        return per, lo, min(nq, lo + per)
+
+    def knn2(self, q):
+        """Every rank passes the SAME full query set and returns the full, identical result."""
+        import torch
+        import torch.distributed as dist
+        nq, dev = q.shape[0], q.device
+        per, lo, hi = self.slice_bounds(nq)
+        pad = per * self.world
+        b = self._bufs
+        if b is None or b[0].shape[0] != pad or b[0].device != dev:
+            b = self._bufs = (torch.empty((pad, 2), dtype=torch.int32, device=dev),
+                              torch.empty((pad, 2), dtype=torch.int32, device=dev),
+                              torch.empty((pad,), dtype=torch.uint8, device=dev))
+        idx, dist_, acc = b
+        if self.cross_check and self.world > 1:
+            raise ValueError("cross-check needs every query on one rank: the reverse search ranks ALL queries of a train row")
+        self._knn2_slice(q[lo:hi], idx[lo:hi], dist_[lo:hi], acc[lo:hi])
+        if self.world > 1:
+            # in place: this rank's slice already sits at its offset of the gathered arrays
+            r0 = self.rank * per
+            for x in (idx, dist_, acc):
+                dist.all_gather_into_tensor(x, x[r0:r0 + per], group=self.group)
+            self.last_exchange = "in-place all-gather of the finished results (no candidate exchange)"
+        return idx[:nq], dist_[:nq], acc[:nq]
+
+    def knn2_host(self, q_host, train_host=None):
+        """Host form: this rank uploads ITS query slice only (and, optionally, the replicated train set again); the gathered
+        result is read back in one packed copy."""
+        import numpy as np
+        import torch
+        dev = self.train.device
+        if train_host is not None:
+            self.train.copy_(torch.from_numpy(train_host) if isinstance(train_host, np.ndarray) else train_host, non_blocking=True)
+        qh = torch.from_numpy(q_host) if isinstance(q_host, np.ndarray) else q_host
+        nq = qh.shape[0]
+        per, lo, hi = self.slice_bounds(nq)
+        qd = self._host_q
+        if qd is None or qd.shape[0] != nq or qd.device != dev:
+            qd = self._host_q = torch.empty((nq,) + tuple(qh.shape[1:]), dtype=qh.dtype, device=dev)
+        qd[lo:hi].copy_(qh[lo:hi], non_blocking=True)
+        idx, dist_, acc = self.knn2(qd)
+        packed = torch.empty((nq, 17), dtype=torch.uint8, device=dev)
+        packed[:, 0:8] = idx.view(torch.uint8).view(nq, 8)
+        packed[:, 8:16] = dist_.view(torch.uint8).view(nq, 8)
+        packed[:, 16] = acc
+        h = packed.cpu().numpy()
+        return (h[:, 0:8].copy().view(np.int32).reshape(nq, 2), h[:, 8:16].copy().view(np.int32).reshape(nq, 2),
+                h[:, 16].copy())
+
+    _host_q = None

@@ -28,7 +28,7 @@ def _worker(rank, world, port, out_dir, exchange):
     import torch.distributed as dist
     import slammatch
     from slammatch import synth
-    from slammatch.sharded import ShardedMatcher, shard_bounds
+    from slammatch.sharded import QueryShardedMatcher, ShardedMatcher, shard_bounds
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -48,6 +48,16 @@ def _worker(rank, world, port, out_dir, exchange):
             used[name] = sm.last_exchange
             np.savez(os.path.join(out_dir, f"{name}_rank{rank}.npz"), idx=idx.cpu().numpy(), dist=dd.cpu().numpy(),
                      acc=acc.cpu().numpy())
+            if name == "c4like" and exchange == "auto":
+                # the other decomposition of the same search: train set replicated, queries sliced, results all-gathered;
+                # a ragged query count (the last slices are shorter / empty)
+                qs = QueryShardedMatcher(torch.from_numpy(t).cuda(), ratio=(7, 10))
+                for n_q in (nq, 5, nq - 3):
+                    for _ in range(2):
+                        qi, qd_, qa = qs.knn2(qd[:n_q])
+                    torch.cuda.synchronize()
+                    assert torch.equal(qi, idx[:n_q]) and torch.equal(qd_, dd[:n_q]) and torch.equal(qa, acc[:n_q]), n_q
+                assert "all-gather" in qs.last_exchange
         # the sharded keyframe DB (round-robin keyframes, rebased keys) on the same ranks
         frames = [synth.uniform(n, 4000 + i) for i, n in enumerate((700, 3, 1200, 0, 64, 900, 333))]
         db = slammatch.ShardedKeyframeDB(device=rank, capacity=256)

@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from slammatch import synth
-from slammatch.sharded import ShardedMatcher, shard_bounds
+from slammatch.sharded import QueryShardedMatcher, ShardedMatcher, shard_bounds
 from oracle import oracle as orc
 
 
@@ -64,6 +64,20 @@ def _worker(rank, world, port, q, t, out_dir):
         assert np.array_equal(np.asarray(aa), np.asarray(acc))
         ai, ad, aa = sa.knn2(torch.from_numpy(q[:1]))          # fewer queries than ranks
         assert np.array_equal(np.asarray(ai), np.asarray(idx)[:1]) and np.array_equal(np.asarray(aa), np.asarray(acc)[:1])
+        # query-sharded form: train set replicated, query slices, in-place all-gather of the finished results
+        def knn2_slice(qq, o_idx, o_dist, o_acc):
+            if qq.shape[0]:
+                i, d = orc.np_knn2(qq.numpy(), t)
+                o_idx.copy_(torch.from_numpy(i))
+                o_dist.copy_(torch.from_numpy(d))
+                o_acc.copy_(torch.from_numpy(orc.np_ratio(d, 7, 10)))
+
+        qs = QueryShardedMatcher(torch.from_numpy(t), knn2_slice=knn2_slice)
+        assert qs.world == world and qs.rank == rank
+        for n_q in (q.shape[0], q.shape[0] - 1, 1):
+            qi, qd, qa = qs.knn2(torch.from_numpy(q[:n_q]))
+            assert np.array_equal(np.asarray(qi), np.asarray(idx)[:n_q]) and np.array_equal(np.asarray(qd), np.asarray(dd)[:n_q])
+            assert np.array_equal(np.asarray(qa), np.asarray(acc)[:n_q])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx, dist=dd, acc=acc)
     finally:
         dist.destroy_process_group()
