@@ -855,88 +855,138 @@ __global__ void __launch_bounds__(256) tc_chunk_keys_kernel(TcParams p, long lon
     slm_exchange_publish(ex, wrote, 0);
 }
 
-__global__ void __launch_bounds__(256) tc_refine_owned_kernel(TcParams p, long long base, slm_exchange ex)
+// The usual plan (one unit, one epoch per group: four candidates per query): ONE THREAD per query -- a float top-2 of the four
+// packed keys, two conversions, and a coalesced 8- or 16-byte store per peer (a warp's stores to one peer are one run).
+__global__ void __launch_bounds__(256) tc_chunk_keys_flat_kernel(TcParams p, long long base, slm_exchange ex)
 {
-    constexpr int G = 8, kQPW = 4, kQPB = 32;
-    __shared__ ulonglong2 s_keys[kQPB];
+    slm_pdl_launch_dependents();
+    slm_pdl_wait();                                        // the candidate keys of the search kernel are visible from here
+    const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (q < p.nq) {
+        const float4 c4 = reinterpret_cast<const float4 *>(p.cand)[q];
+        const float ca = fmaxf(c4.x, c4.y), cb = fminf(c4.x, c4.y), cc = fmaxf(c4.z, c4.w), cd = fminf(c4.z, c4.w);
+        const float f1 = fmaxf(ca, cc), f2 = fmaxf(fminf(ca, cc), fmaxf(cb, cd));
+        // (dot + 257) << 32 | ~first GLOBAL row of the chunk
+        auto chunk_key = [&](float f) -> unsigned long long {
+            if (!(f > -1.0e30f)) return 0ull;
+            const int ki = (int)f + kKeyBias;
+            const unsigned first_row = (unsigned)(base + (long long)(kChunkMask - (ki & kChunkMask)) * p.chunk);
+            return ((unsigned long long)((ki >> kChunkBits) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - first_row);
+        };
+        const unsigned long long k1 = chunk_key(f1), k2 = chunk_key(f2);
+        for (int r = 0; r < ex.world; ++r) slm_exchange_store_chunks_to(ex, r, q, k1, k2);
+    }
+    slm_exchange_publish(ex, true, 0);
+}
+
+// Tiles of 256 queries per block.  (A) one thread per query reads every rank's two chunk keys (coalesced), keeps the global
+// best two chunks and queues those that lie in THIS rank's row block as work items; (B) the items -- on average 2 / world per
+// query -- are re-scored densely, 8 lanes per item; (C) one thread per query combines its items and stores the exact keys to
+// every peer (coalesced).  Only owned chunks cost anything: the re-scoring is shared between the ranks, not repeated.
+constexpr int kOwnedTile = 256;
+__global__ void __launch_bounds__(kOwnedTile) tc_refine_owned_kernel(TcParams p, long long base, slm_exchange ex)
+{
+    constexpr int G = 8, U = 5;
+    __shared__ uint2 s_first[kOwnedTile];          // first global rows of the query's best two chunks (lower rows first)
+    __shared__ uint4 s_item[kOwnedTile];           // exact (k1, k2) of chunk 0 and of chunk 1, 0xFFFFFFFF = none
+    __shared__ unsigned short s_queue[2 * kOwnedTile];
+    __shared__ int s_n;
     slm_pdl_launch_dependents();
     if (!slm_exchange_wait_flags(ex, 0)) return;          // a lost peer: reported; this rank publishes nothing either
-    const int lane = threadIdx.x & 31, sub = lane % G;
+    const int tid = threadIdx.x, sub = tid % G, grp = tid / G;
     const long long n_q = p.nq;
-    bool wrote = false;
-    for (long long q0 = (long long)blockIdx.x * kQPB; q0 < n_q; q0 += (long long)gridDim.x * kQPB) {
-        const long long gq = q0 + (threadIdx.x >> 5) * kQPW + lane / G;
+    const uint4 *t4 = reinterpret_cast<const uint4 *>(p.t);
+    const unsigned last = (unsigned)max(p.nt, 1) - 1u;
+    for (long long q0 = (long long)blockIdx.x * kOwnedTile; q0 < n_q; q0 += (long long)gridDim.x * kOwnedTile) {
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        // ---- (A) ----
+        const long long gq = q0 + tid;
         const bool live = gq < n_q;
-        const long long gqc = live ? gq : 0;
-        // the global best two chunks of this query out of every rank's two
-        unsigned long long c1 = 0, c2 = 0;
-        for (int i = sub; i < 2 * ex.world; i += G) {
-            unsigned long long c;
-            if (ex.key_bytes == 4) {
-                const unsigned *g = reinterpret_cast<const unsigned *>(ex.peer_keys[ex.rank]) + (slm_exchange_slot(ex, 0, i >> 1) + gqc) * 2;
-                c = slm_chunk_widen(g[i & 1]);
-            } else {
-                const unsigned long long *g = reinterpret_cast<const unsigned long long *>(ex.peer_keys[ex.rank]) +
-                                              (slm_exchange_slot(ex, 0, i >> 1) + gqc) * 2;
-                c = g[i & 1];
+        unsigned flo = 0xFFFFFFFFu, fhi = 0xFFFFFFFFu;
+        if (live) {
+            unsigned long long c1 = 0, c2 = 0;
+            for (int i = 0; i < ex.world; ++i) {
+                const long long slot = slm_exchange_slot(ex, 0, i) + gq;
+                if (ex.key_bytes == 4) {
+                    const uint2 g = reinterpret_cast<const uint2 *>(ex.peer_keys[ex.rank])[slot];
+                    top2_insert_max(c1, c2, slm_chunk_widen(g.x));
+                    top2_insert_max(c1, c2, slm_chunk_widen(g.y));
+                } else {
+                    const ulonglong2 g = reinterpret_cast<const ulonglong2 *>(ex.peer_keys[ex.rank])[slot];
+                    top2_insert_max(c1, c2, g.x);
+                    top2_insert_max(c1, c2, g.y);
+                }
             }
-            top2_insert_max(c1, c2, c);
-        }
+            const unsigned fa = c1 ? 0xFFFFFFFFu - (unsigned)(c1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+            const unsigned fb = c2 ? 0xFFFFFFFFu - (unsigned)(c2 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+            flo = min(fa, fb);
+            fhi = max(fa, fb);
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, c1, o);
-            const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, c2, o);
-            top2_insert_max(c1, c2, o1);
-            top2_insert_max(c1, c2, o2);
+            for (int sel = 0; sel < 2; ++sel) {
+                const unsigned f = sel ? fhi : flo;
+                if (f != 0xFFFFFFFFu && (long long)f >= base && (long long)f < base + p.nt)
+                    s_queue[atomicAdd(&s_n, 1)] = (unsigned short)(tid * 2 + sel);
+            }
         }
-        const unsigned fa = c1 ? 0xFFFFFFFFu - (unsigned)(c1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
-        const unsigned fb = c2 ? 0xFFFFFFFFu - (unsigned)(c2 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
-        const unsigned flo = min(fa, fb), fhi = max(fa, fb);         // first global rows; 0xFFFFFFFF = no such chunk
-        const uint4 *qs = reinterpret_cast<const uint4 *>(p.q + gqc * 8);
-        const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
-        unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        s_first[tid] = make_uint2(flo, fhi);
+        s_item[tid] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        __syncthreads();
+        // ---- (B) ----
+        const int n_items = s_n;
+        for (int it = grp; it < n_items; it += kOwnedTile / G) {
+            const int item = s_queue[it], ql = item >> 1, sel = item & 1;
+            const unsigned f = sel ? s_first[ql].y : s_first[ql].x;
+            const unsigned row0 = (unsigned)((long long)f - base);
+            const uint4 *qs = reinterpret_cast<const uint4 *>(p.q + (q0 + ql) * 8);
+            const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
+            unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+            for (int pos0 = sub; pos0 < p.chunk; pos0 += U * G) {
+                uint4 ta[U], tb[U];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const unsigned f = s == 0 ? flo : fhi;
-            // only the owner of a chunk re-scores it
-            if (f == 0xFFFFFFFFu || (long long)f < base || (long long)f >= base + p.nt) continue;
-            const long long row0 = (long long)f - base;
-            for (int pos = sub; pos < p.chunk; pos += G) {
-                const long long row = row0 + pos;
-                if (row < p.nt) {
-                    const uint4 *ts = reinterpret_cast<const uint4 *>(p.t + row * 8);
-                    const unsigned key = refine_key(hamming256(qa, qb, __ldg(ts), __ldg(ts + 1)), s, pos);
+                for (int u = 0; u < U; ++u) {
+                    const uint4 *ts = t4 + 2ull * min(row0 + (unsigned)(pos0 + u * G), last);
+                    ta[u] = __ldg(ts);
+                    tb[u] = __ldg(ts + 1);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int pos = pos0 + u * G;
+                    unsigned key = (hamming256(qa, qb, ta[u], tb[u]) << 8) | ((unsigned)sel << 7) | (unsigned)pos;
+                    key = (pos < p.chunk && row0 + (unsigned)pos < (unsigned)p.nt) ? key : 0xFFFFFFFFu;
                     const unsigned m = max(k1, key);
                     k1 = min(k1, key);
                     k2 = min(k2, m);
                 }
             }
-        }
+            // the four groups of a warp run different numbers of items: the shuffles name the group's own 8 lanes only
+            const unsigned gmask = 0xFFu << ((tid & 31) & ~(G - 1));
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            const unsigned o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o);
-            const unsigned o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
-            unsigned m = max(k1, o1);
-            k1 = min(k1, o1);
-            k2 = min(min(k2, o2), m);
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const unsigned o1 = __shfl_xor_sync(gmask, k1, o), o2 = __shfl_xor_sync(gmask, k2, o);
+                const unsigned m = max(k1, o1);
+                k1 = min(k1, o1);
+                k2 = min(min(k2, o2), m);
+            }
+            if (sub == 0) {
+                if (sel) { s_item[ql].z = k1; s_item[ql].w = k2; }
+                else { s_item[ql].x = k1; s_item[ql].y = k2; }
+            }
         }
-        if (live && sub == 0) {
+        __syncthreads();
+        // ---- (C) ----
+        if (live) {
+            const uint4 r = s_item[tid];
+            const unsigned k1 = min(r.x, r.z), k2 = min(max(r.x, r.z), min(r.y, r.w));
             auto widen = [&](unsigned k) -> unsigned long long {
                 if (k == 0xFFFFFFFFu) return kKeyNone;
                 return ((unsigned long long)(k >> 8) << 32) | (unsigned long long)(((k & 128u) ? fhi : flo) + (k & 127u));
             };
-            s_keys[(threadIdx.x >> 5) * kQPW + lane / G] = make_ulonglong2(widen(k1), widen(k2));
+            const unsigned long long w1 = widen(k1), w2 = widen(k2);
+            for (int pr = 0; pr < ex.world; ++pr) slm_exchange_store_to(ex, pr, gq, w1, w2, 1);
         }
-        __syncthreads();
-        const int n_here = (int)min((long long)kQPB, n_q - q0);
-        for (int i = threadIdx.x; i < n_here * ex.world; i += blockDim.x) {
-            const int r = i / n_here, k = i - r * n_here;
-            slm_exchange_store_to(ex, r, q0 + k, s_keys[k].x, s_keys[k].y, 1);
-            wrote = true;
-        }
-        __syncthreads();
     }
-    slm_exchange_publish(ex, wrote, 1);
+    slm_exchange_publish(ex, true, 1);
 }
 
 // Refine for batches of frame-sized problems (config 3).  tc_refine_kernel reads every query's candidate rows
@@ -1230,13 +1280,15 @@ int tc_run(slm_ctx *ctx, TcParams p, int n_prob, long long base, uint64_t *keys_
         // sharded, many queries: agree on the global best two chunks first, only their owners refine them
         const bool few = p.cpg * p.n_epochs * 4 <= 32;
         const int iters = n_q >= 65536 ? kRefineMaxIters : 1;
-        if (few)
+        if (p.cpg * p.n_epochs == 1)
+            SLM_CUDA(slm_launch(tc_chunk_keys_flat_kernel, dim3((unsigned)((n_q + 255) / 256)), dim3(256), 0, stream, pdl, p, base, ex));
+        else if (few)
             SLM_CUDA(slm_launch(tc_chunk_keys_kernel<8>, dim3((unsigned)((n_q + 32 * iters - 1) / (32 * iters))), dim3(256), 0, stream,
                                 pdl, p, base, ex, iters));
         else
             SLM_CUDA(slm_launch(tc_chunk_keys_kernel<32>, dim3((unsigned)((n_q + 8 * iters - 1) / (8 * iters))), dim3(256), 0, stream,
                                 pdl, p, base, ex, iters));
-        long long blocks = (n_q + 31) / 32, cap = 4 * ctx->exchange_max_blocks;
+        long long blocks = (n_q + kOwnedTile - 1) / kOwnedTile, cap = 4 * ctx->exchange_max_blocks;
         if (blocks > cap) blocks = cap;
         SLM_CUDA(slm_launch(tc_refine_owned_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, pdl, p, base, ex));
         ctx->launches += 1;
