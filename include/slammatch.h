@@ -125,6 +125,18 @@ int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q_dev, int64_t nq, const uint3
                     int32_t *idx_out_dev, int32_t *dist_out_dev, uint8_t *accept_out_dev, void *stream);
 
 /*
+ * knnMatch(q, t, k=2, mask=M) -- the optional `mask` argument of OpenCV's DescriptorMatcher::knnMatch, which the matcher
+ * object built at tracking.py:17 / keypoint.py:43 / Point3D.py:39 accepts (the reference itself never passes one).
+ * mask_dev is uint8[nq][mask_row_stride] on the device, mask_row_stride >= nt; pair (i, j) takes part iff
+ * mask_dev[i * mask_row_stride + j] != 0.  A query with fewer than two allowed rows gets idx/dist = -1 in the missing
+ * columns (the binding turns them into a short DMatch row, as OpenCV does).  Ratio test as in slm_knn2_filter; there is
+ * no cross-check (OpenCV asserts mask.empty() when crossCheck is set, batch_distance.cpp:303).
+ */
+int slm_knn2_masked(slm_ctx *ctx, const uint32_t *q_dev, int64_t nq, const uint32_t *t_dev, int64_t nt,
+                    int64_t train_index_base, const uint8_t *mask_dev, int64_t mask_row_stride, int32_t ratio_num,
+                    int32_t ratio_den, int32_t *idx_out_dev, int32_t *dist_out_dev, uint8_t *accept_out_dev, void *stream);
+
+/*
  * Config 3 (local-mapping batch): desc_dev is uint32[n_frames][n_per_frame][8]; pairs_host is a HOST
  * array int32[n_pairs][2] of (query frame, train frame).  Outputs are [n_pairs][n_per_frame][2] /
  * [n_pairs][n_per_frame]; train indices are local to the train frame.

@@ -100,6 +100,37 @@ def np_knn2(q, t, train_index_base: int = 0):
     return keys_to_idx_dist(np_knn2_keys(q, t, train_index_base))
 
 
+def np_knn2_masked(q, t, mask, train_index_base: int = 0):
+    """knnMatch(q, t, k=2, mask=mask) restated: pair (i, j) takes part iff mask[i, j] != 0 (OpenCV's
+    DescriptorMatcher mask); a query with fewer than two allowed rows gets -1 in
+    the missing columns (OpenCV returns a short row).  Order (distance, trainIdx) as in np_knn2_keys."""
+    q = _as_desc(q)
+    t = _as_desc(t)
+    nq, nt = q.shape[0], t.shape[0]
+    keys = np.full((nq, 2), NONE_KEY, dtype=np.uint64)
+    if nq and nt:
+        mask = np.asarray(mask)
+        if mask.shape != (nq, nt) or mask.dtype != np.uint8:
+            raise ValueError("mask must be uint8[nq, nt]")
+        q64, t64 = q.view(np.uint64), t.view(np.uint64)
+        col = np.arange(nt, dtype=np.uint64) + np.uint64(train_index_base)
+        rows = max(1, (1 << 22) // nt)
+        for s in range(0, nq, rows):
+            qs = q64[s:s + rows]
+            d = np.zeros((qs.shape[0], nt), dtype=np.uint64)
+            for w in range(4):
+                d += np.bitwise_count(qs[:, w:w + 1] ^ t64[None, :, w]).astype(np.uint64)
+            key = (d << np.uint64(32)) | col[None, :]
+            key[mask[s:s + rows] == 0] = NONE_KEY
+            if nt == 1:
+                keys[s:s + rows, 0] = key[:, 0]
+            else:
+                part = np.partition(key, 1, axis=1)[:, :2]
+                part.sort(axis=1)
+                keys[s:s + rows] = part
+    return keys_to_idx_dist(keys)
+
+
 def np_ratio(dist, num: int, den: int) -> np.ndarray:
     """Integer form of ``m.distance < ratio * n.distance`` (tracking.py:27): den*d1 < num*d2."""
     dist = np.asarray(dist, dtype=np.int64)
@@ -315,6 +346,20 @@ def cv_knn2(q, t, train_index_base: int = 0):
         k[i < 0] = NONE_KEY
         parts.append(k)
     return keys_to_idx_dist(np_merge_top2(np.stack(parts)))
+
+
+def cv_knn2_masked(q, t, mask):
+    """cv2.BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2, mask=mask) as (idx, dist) with -1 padding."""
+    import cv2
+    q = _as_desc(q)
+    t = _as_desc(t)
+    nq, nt = q.shape[0], t.shape[0]
+    if nq == 0 or nt == 0:
+        return np.full((nq, 2), -1, np.int32), np.full((nq, 2), -1, np.int32)
+    if nt > CV_MAX_TRAIN_ROWS:
+        raise ValueError("cv_knn2_masked: train set too long for one OpenCV call")
+    rows = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2, mask=np.ascontiguousarray(mask, dtype=np.uint8))
+    return dmatch_rows_to_arrays(rows, nq)
 
 
 def cv_cross_check_pairs(q, t):

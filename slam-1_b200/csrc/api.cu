@@ -392,6 +392,35 @@ int slm_knn2_filter(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t 
     return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
 }
 
+int slm_knn2_masked(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                    const uint8_t *mask, int64_t mask_row_stride, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out,
+                    int32_t *dist_out, uint8_t *accept_out, void *stream_)
+{
+    SLM_TRY(check_ctx(ctx));
+    SLM_TRY(check_sizes(nq, nt, base));
+    if (ratio_num > 0 && ratio_den <= 0) return slm_fail(SLM_ERR_INVALID, "ratio_den must be > 0");
+    if (nq == 0) return SLM_OK;
+    if (!q || (nt > 0 && (!t || !mask))) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
+    if (mask_row_stride < nt) return slm_fail(SLM_ERR_INVALID, "mask_row_stride (%lld) < nt (%lld)", (long long)mask_row_stride,
+                                              (long long)nt);
+    if (((uintptr_t)q & 15) || ((uintptr_t)t & 15))
+        return slm_fail(SLM_ERR_INVALID, "descriptor pointers must be 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SLM_TRY(slm_enter(ctx, stream));
+    SLM_TRY(slm_prof_mark(ctx, stream, SLM_TAG_CALL_BEGIN));
+    if (nt == 0) {
+        // empty train set: every row is empty, exactly like the unmasked call
+        SLM_TRY(slm_buf_reserve(ctx, &ctx->keys, (size_t)nq * 16));
+        uint64_t *keys = reinterpret_cast<uint64_t *>(ctx->keys.p);
+        SLM_TRY(knn2_keys_dispatch(ctx, q, nq, t, nt, base, keys, stream));
+        SLM_TRY(slm_finalize(ctx, keys, nq, ratio_num, ratio_den, nullptr, nt, base, idx_out, dist_out, accept_out, stream));
+    } else {
+        SLM_TRY(slm_masked_knn2(ctx, q, nq, t, nt, base, mask, mask_row_stride, ratio_num, ratio_den, idx_out, dist_out,
+                                accept_out, stream));
+    }
+    return slm_prof_mark(ctx, stream, SLM_TAG_CALL_END);
+}
+
 int slm_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
              int32_t *idx_out, int32_t *dist_out, void *stream)
 {

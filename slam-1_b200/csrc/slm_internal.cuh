@@ -141,6 +141,11 @@ int slm_popc_knn2_keys_batched(slm_ctx *ctx, const uint32_t *desc, int64_t n_per
 int slm_stream_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt,
                          int64_t base, uint64_t *keys_out, cudaStream_t stream);
 
+// ---- masked search: knnMatch(q, t, k=2, mask=M), M uint8[nq][nt] with row stride mask_stride (knn2_masked.cu) ------
+int slm_masked_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t *t, int64_t nt, int64_t base,
+                    const uint8_t *mask, int64_t mask_stride, int32_t ratio_num, int32_t ratio_den, int32_t *idx_out,
+                    int32_t *dist_out, uint8_t *accept_out, cudaStream_t stream);
+
 // ---- frame-to-frame shapes in one launch: search + merge + ratio (+ cross-check) (knn2_frame.cu) ------------
 // keys_out (uint64[nq][2]) and idx/dist/accept are each optional; cross-check needs accept_out.
 bool slm_frame_eligible(slm_ctx *ctx, int64_t nq, int64_t nt, bool cross);

@@ -20,7 +20,7 @@ SYMBOLS = (
     "slm_last_error", "slm_version", "slm_create", "slm_destroy", "slm_set_variant", "slm_last_variant",
     "slm_launch_count", "slm_last_kernel",
     "slm_profile_enable", "slm_profile_read",
-    "slm_knn2", "slm_knn2_keys", "slm_knn2_filter", "slm_knn2_batched", "slm_merge_top2",
+    "slm_knn2", "slm_knn2_keys", "slm_knn2_filter", "slm_knn2_masked", "slm_knn2_batched", "slm_merge_top2",
     "slm_exchange_merge", "slm_knn2_exchange", "slm_exchange_status",
     "slm_compact_matches", "slm_gather_rows", "slm_filter_points3d", "slm_bow_hist", "slm_chi2_scan", "slm_vocab_update",
     "slm_knn2_host", "slm_probe_tensor_peak", "slm_probe_popc_peak",
@@ -68,6 +68,7 @@ def load():
         lib.slm_knn2.argtypes = [vp, vp, i64, vp, i64, i64, vp, vp, vp]
         lib.slm_knn2_keys.argtypes = [vp, vp, i64, vp, i64, i64, vp, vp]
         lib.slm_knn2_filter.argtypes = [vp, vp, i64, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp]
+        lib.slm_knn2_masked.argtypes = [vp, vp, i64, vp, i64, i64, vp, i64, i32, i32, vp, vp, vp, vp]
         lib.slm_knn2_batched.argtypes = [vp, vp, i64, i64, vp, i64, i32, i32, vp, vp, vp, vp]
         lib.slm_merge_top2.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, vp]
         lib.slm_exchange_merge.argtypes = [vp, vp, i64, i64, i64, vp, vp, i32, i32, ctypes.c_uint32, i32, i32, vp, vp, vp, vp]

@@ -101,14 +101,20 @@ def _is_torch_cuda(x) -> bool:
 
 
 def knn2(q, t, ratio=REFERENCE_RATIO, cross_check: bool = False, device: int | None = None,
-         train_index_base: int = 0, variant: str | None = None):
+         train_index_base: int = 0, variant: str | None = None, mask=None):
     """Exact Hamming 2-NN of every row of ``q`` in ``t`` + Lowe ratio (+ cross-check).
 
     Returns ``idx int32[nq, 2]``, ``dist int32[nq, 2]``, ``accept uint8[nq]`` -- numpy arrays for numpy
     inputs, CUDA tensors for CUDA-tensor inputs.  ``ratio=(num, den)`` is the integer form of the
-    reference's ``m.distance < r * n.distance``; ``None`` disables it.
+    reference's ``m.distance < r * n.distance``; ``None`` disables it.  ``mask`` (optional, ``uint8[nq, nt]``,
+    OpenCV's ``knnMatch(..., mask=)``): only pairs with a non-zero entry take part; missing neighbours are -1.
     """
     num, den = _ratio_args(ratio)
+    if mask is not None:
+        if cross_check:
+            # OpenCV: batch_distance.cpp:303 asserts mask.empty() when crossCheck is set
+            raise ValueError("mask= cannot be combined with cross-check (as in OpenCV)")
+        return _knn2_masked(q, t, mask, num, den, 0 if device is None else device, train_index_base)
     if _is_torch_cuda(q) or _is_torch_cuda(t):
         return _knn2_device(q, t, num, den, cross_check, train_index_base, variant)
     q = _as_desc(q, "queryDescriptors")
@@ -160,6 +166,45 @@ def _knn2_device(q, t, num, den, cross_check, base, variant):
     return idx, dist, acc
 
 
+def _knn2_masked(q, t, mask, num, den, device, base):
+    """``knnMatch(q, t, k=2, mask=mask)`` through ``slm_knn2_masked`` (one integer-pipe kernel; the mask, one byte per
+    pair, is the largest operand).  Host arrays are staged through torch; the result comes back in the inputs' kind."""
+    import torch
+    on_device = _is_torch_cuda(q) or _is_torch_cuda(t) or _is_torch_cuda(mask)
+    if on_device:
+        qd, td = _dev_desc(q, "queryDescriptors"), _dev_desc(t, "trainDescriptors")
+        if not _is_torch_cuda(mask):
+            raise ValueError("mask: mixing host and device inputs is not supported")
+        dev = qd.device
+    else:
+        qh, th = _as_desc(q, "queryDescriptors"), _as_desc(t, "trainDescriptors")
+        mask = np.asarray(mask)
+    nq = (qd if on_device else qh).shape[0]
+    nt = (td if on_device else th).shape[0]
+    # OpenCV (matchers.cpp:639): masks[i].type() == CV_8UC1 && rows == queryDescriptorsCount && cols == train rows
+    if tuple(mask.shape) != (nq, nt) or mask.dtype != (torch.uint8 if on_device else np.uint8):
+        raise ValueError(f"mask: expected uint8[{nq}, {nt}], got {mask.dtype} {tuple(mask.shape)}")
+    if not on_device:
+        dev = torch.device("cuda", device)
+        if not torch.cuda.is_available():
+            raise _lib.SlamMatchError(-2, "CUDA device required: there is no CPU path")
+        qd, td = torch.from_numpy(qh).to(dev), torch.from_numpy(th).to(dev)
+        mask = torch.from_numpy(np.ascontiguousarray(mask)).to(dev)
+    md = mask.contiguous()
+    ctx = _lib.context(dev.index or 0)
+    idx = torch.full((nq, 2), -1, dtype=torch.int32, device=dev)
+    dist = torch.full((nq, 2), -1, dtype=torch.int32, device=dev)
+    acc = torch.zeros((nq,), dtype=torch.uint8, device=dev)
+    if nq:
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(ctx.lib.slm_knn2_masked(ctx.handle, qd.data_ptr(), nq, td.data_ptr() if nt else None, nt, int(base),
+                                           md.data_ptr() if nt else None, nt, num, den, idx.data_ptr(), dist.data_ptr(),
+                                           acc.data_ptr(), stream))
+    if on_device:
+        return idx, dist, acc
+    return idx.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy()
+
+
 class Matcher:
     """Drop-in for the object built by ``cv2.FlannBasedMatcher(indexParams=..., searchParams=...)``.
 
@@ -208,10 +253,13 @@ class Matcher:
         return flat, np.concatenate([[0], np.cumsum(sizes)])
 
     # -- the hot path ----------------------------------------------------------------------------
-    def knnMatch(self, queryDescriptors, trainDescriptors=None, k: int = 2, mask=None, compactResult: bool = False):
-        """``matcher.knnMatch(des1, des2, k=2)`` (tracking.py:22): tuple[nq] of tuple[min(k, nt)] of DMatch."""
-        if mask is not None:
-            raise NotImplementedError("mask= is not on the reference's path and is not supported")
+    def knnMatch(self, queryDescriptors, trainDescriptors=None, k: int = 2, mask=None, compactResult: bool = False,
+                 masks=None):
+        """``matcher.knnMatch(des1, des2, k=2)`` (tracking.py:22): tuple[nq] of tuple[min(k, nt)] of DMatch.
+
+        ``mask`` (``uint8[nq, nt]``; with a collection: ``masks=[uint8[nq, n_i], ...]``, one per added image) restricts the
+        search to the pairs with a non-zero entry, as in OpenCV; rows then hold as many neighbours as were allowed (up to k)
+        and ``compactResult=True`` drops the empty ones."""
         if isinstance(trainDescriptors, (int, np.integer)) and k == 2:  # knnMatch(q, k) positional form
             trainDescriptors, k = None, int(trainDescriptors)
         if k not in (1, 2):
@@ -219,6 +267,8 @@ class Matcher:
         if self.crossCheck and k != 1:
             # OpenCV: batch_distance.cpp:303 asserts K == 1 when crossCheck is set
             raise ValueError("crossCheck=True requires k == 1 (as in OpenCV); use knn2(cross_check=True) for kNN-2 + cross-check")
+        if mask is not None or masks:
+            return self._knn_match_masked(queryDescriptors, trainDescriptors, k, mask, masks, compactResult)
         q = _as_desc(queryDescriptors, "queryDescriptors")
         if trainDescriptors is None and self._db is not None and q.shape[0] > 0:
             # resident collection: only the query crosses PCIe
@@ -230,6 +280,27 @@ class Matcher:
             t, offsets = _as_desc(trainDescriptors, "trainDescriptors"), None
         idx, dist, acc = knn2(q, t, ratio=None, cross_check=self.crossCheck, device=self.device, variant=self.variant)
         return self._rows(idx, dist, acc if self.crossCheck else None, k, offsets)
+
+    def _knn_match_masked(self, queryDescriptors, trainDescriptors, k, mask, masks, compact):
+        if self.crossCheck:
+            # OpenCV: batch_distance.cpp:303 asserts mask.empty() when crossCheck is set
+            raise ValueError("mask= cannot be combined with crossCheck=True (as in OpenCV)")
+        q = _as_desc(queryDescriptors, "queryDescriptors")
+        if trainDescriptors is None:
+            t, offsets = self._collection()
+            if mask is not None and masks is None:
+                masks = [mask]
+            if len(masks) != len(self._train):
+                raise ValueError(f"masks: expected one mask per added image ({len(self._train)}), got {len(masks)}")
+            for m, d in zip(masks, self._train):
+                if np.asarray(m).shape != (q.shape[0], d.shape[0]):
+                    raise ValueError(f"masks: expected uint8[{q.shape[0]}, {d.shape[0]}], got {np.asarray(m).shape}")
+            mask = np.concatenate([np.asarray(m) for m in masks], axis=1) if masks else np.zeros((q.shape[0], 0), np.uint8)
+        else:
+            t, offsets = _as_desc(trainDescriptors, "trainDescriptors"), None
+        idx, dist, _ = knn2(q, t, ratio=None, device=self.device, mask=mask)
+        rows = self._rows(idx, dist, None, k, offsets)
+        return tuple(r for r in rows if r) if compact else rows
 
     def match(self, queryDescriptors, trainDescriptors=None, mask=None):
         """Best neighbour per query as a flat list (``DescriptorMatcher.match``); honours crossCheck."""

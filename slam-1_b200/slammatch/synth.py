@@ -54,3 +54,32 @@ def with_duplicates(t: np.ndarray, seed: int, frac: float = 0.2) -> np.ndarray:
         src = rng.integers(0, n, size=k)
         t[dst] = t[src]
     return t
+
+
+def match_mask(nq: int, nt: int, seed: int, kind: str = "half") -> np.ndarray:
+    """Masks for ``knnMatch(..., mask=)``: uint8[nq, nt], pair (i, j) allowed iff the entry is non-zero.
+
+    ``half``: every pair allowed with probability 1/2, values drawn from {1, 7, 255} (any non-zero byte counts);
+    ``sparse``: ~3 allowed rows per query, and every fifth query has none / exactly one / exactly two allowed rows in turn
+    (the short-row cases); ``band``: only |i * nt / nq - j| <= 8 (a spatial search window); ``ones`` / ``zeros``.
+    """
+    rng = np.random.default_rng(seed)
+    if kind == "ones":
+        return np.ones((nq, nt), np.uint8)
+    if kind == "zeros":
+        return np.zeros((nq, nt), np.uint8)
+    if kind == "half":
+        m = rng.random((nq, nt)) < 0.5
+        return (m * rng.choice(np.array([1, 7, 255], np.uint8), size=(nq, nt))).astype(np.uint8)
+    if kind == "sparse":
+        m = (rng.random((nq, nt)) < min(1.0, 3.0 / max(nt, 1))).astype(np.uint8)
+        for i in range(0, nq, 5):
+            m[i] = 0
+            n_allowed = (i // 5) % 3
+            if n_allowed and nt:
+                m[i, rng.choice(nt, size=min(n_allowed, nt), replace=False)] = 1
+        return m
+    if kind == "band":
+        centre = (np.arange(nq, dtype=np.int64) * max(nt, 1)) // max(nq, 1)
+        return (np.abs(centre[:, None] - np.arange(nt, dtype=np.int64)[None, :]) <= 8).astype(np.uint8)
+    raise ValueError(kind)

@@ -60,3 +60,28 @@ def load_knn2_golden():
 @pytest.fixture(scope="session")
 def knn2_golden():
     return load_knn2_golden()
+
+
+def load_masked_golden():
+    """Yield (name, q, t, mask, idx, dist) for every committed knnMatch(..., mask=) vector of cv2.BFMatcher
+    (tests/golden/knn2_masked.npz); inputs and masks are regenerated from their seeds and checked by hash."""
+    import hashlib
+    from slammatch import synth
+    z = np.load(os.path.join(GOLDEN, "knn2_masked.npz"))
+    out = []
+    for name in z["names"]:
+        name = str(name)
+        kind, shape, seed, mkind = name.split("_")
+        nq, nt = (int(x) for x in shape.split("x"))
+        seed = int(seed[1:])
+        q, t = golden_inputs(kind, nq, nt, seed)
+        mask = synth.match_mask(nq, nt, seed + 200000, mkind)
+        for a, key in ((q, "sha_q"), (t, "sha_t"), (mask, "sha_mask")):
+            assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() == str(z[f"{name}/{key}"]), (name, key)
+        out.append((name, q, t, mask, z[name + "/idx"], z[name + "/dist"]))
+    return out
+
+
+@pytest.fixture(scope="session")
+def masked_golden():
+    return load_masked_golden()

@@ -5,7 +5,8 @@ The reference ships no golden vectors, so these are produced from
 
   (1) cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2): the exhaustive member of the OpenCV
       matcher family the reference calls at tracking.py:22 / keypoint.py:44 / Point3D.py:40;
-  (2) cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(q, t) for the cross-check definition;
+  (2) cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(q, t) for the cross-check definition, and
+      cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2, mask=M) for the optional mask argument;
   (3) the reference's OWN functions, imported unmodified from /root/reference:
       tracking.get_matches (tracking.py:12-34) and Point3D.find_2D_and_3D_correspondenses
       (Point3D.py:33-54), with ``cv2.FlannBasedMatcher`` rebound to the exhaustive matcher
@@ -108,6 +109,35 @@ def gen_knn2():
     out["cv2_version"] = np.array(cv2.__version__)
     np.savez_compressed(os.path.join(HERE, "knn2_bfmatcher.npz"), **out)
     print("knn2_bfmatcher.npz:", len(names), "cases")
+
+
+# (descriptor kind, nq, nt, seed, mask kind) -- knnMatch(q, t, k=2, mask=M), SURVEY.md section 8(b)/(c)(vii)
+MASK_CASES = [
+    ("uniform", 7, 3, 31, "half"), ("uniform", 5, 1, 32, "half"), ("uniform", 64, 2, 33, "sparse"),
+    ("uniform", 257, 1000, 34, "half"), ("planted", 1000, 1000, 35, "sparse"), ("ties", 257, 1000, 36, "half"),
+    ("ties", 130, 4099, 37, "band"), ("dups", 500, 3000, 38, "band"), ("uniform", 33, 4099, 39, "sparse"),
+    ("uniform", 100, 700, 40, "ones"), ("uniform", 100, 700, 41, "zeros"), ("planted", 2000, 20000, 42, "sparse"),
+    ("ties", 1000, 20000, 43, "half"),
+]
+
+
+def gen_knn2_masked():
+    out, names = {}, []
+    for kind, nq, nt, seed, mkind in MASK_CASES:
+        q, t = make_inputs(kind, nq, nt, seed)
+        mask = synth.match_mask(nq, nt, seed + 200000, mkind)
+        idx, dist = rows_to_arrays(cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2, mask=mask), nq)
+        name = f"{kind}_{nq}x{nt}_s{seed}_{mkind}"
+        names.append(name)
+        out[name + "/idx"] = idx
+        out[name + "/dist"] = dist
+        out[name + "/sha_q"] = np.array(sha(q))
+        out[name + "/sha_t"] = np.array(sha(t))
+        out[name + "/sha_mask"] = np.array(sha(mask))
+    out["names"] = np.array(names)
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(HERE, "knn2_masked.npz"), **out)
+    print("knn2_masked.npz:", len(names), "cases")
 
 
 def gen_ratio_table():
@@ -221,8 +251,11 @@ def gen_reference_stereo():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "stereo":
         gen_reference_stereo()
+    elif len(sys.argv) > 1 and sys.argv[1] == "masked":
+        gen_knn2_masked()
     else:
         gen_knn2()
+        gen_knn2_masked()
         gen_ratio_table()
         gen_reference_functions()
         gen_reference_stereo()

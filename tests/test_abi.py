@@ -40,6 +40,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert b"NULL" in lib.slm_last_error()
     assert lib.slm_set_variant(None, 1) == -1
     assert lib.slm_knn2_host(None, None, 1, None, 1, 7, 10, 0, None, None, None) == -1
+    assert lib.slm_knn2_masked(None, None, 1, None, 1, 0, None, 1, 7, 10, None, None, None, None) == -1
 
 
 def test_no_cpu_fallback_without_cuda():
@@ -62,8 +63,14 @@ def test_matcher_validates_inputs_like_opencv():
         m.knnMatch(good, np.zeros((3, 16), np.uint8), k=2)   # column mismatch
     with pytest.raises(ValueError):
         m.knnMatch(good, good, k=3)
-    with pytest.raises(NotImplementedError):
-        m.knnMatch(good, good, k=2, mask=np.ones((3, 3), np.uint8))
+    with pytest.raises(ValueError):
+        m.knnMatch(good, good, k=2, mask=np.ones((3, 4), np.uint8))   # OpenCV: matchers.cpp:639 asserts the mask's shape
+    with pytest.raises(ValueError):
+        m.knnMatch(good, good, k=2, mask=np.ones((3, 3), np.int32))   # ... and CV_8UC1
+    with pytest.raises(ValueError):
+        slammatch.Matcher(crossCheck=True).knnMatch(good, good, k=1, mask=np.ones((3, 3), np.uint8))  # mask.empty() asserted
+    with pytest.raises(ValueError):
+        slammatch.knn2(good, good, cross_check=True, mask=np.ones((3, 3), np.uint8))
     with pytest.raises(ValueError):
         slammatch.Matcher(crossCheck=True).knnMatch(good, good, k=2)  # OpenCV asserts K == 1
     with pytest.raises(ValueError):
