@@ -92,7 +92,8 @@ def test_nccl_sharded_query_equals_oracle(tmp_path):
     # SLM_TEST_WORLDS=8 restricts the rank counts (the 2-rank pass is also what the single-GPU loopback tests cover)
     worlds = [int(x) for x in os.environ.get("SLM_TEST_WORLDS", "").split(",") if x] or sorted({2, n})
     for world in worlds:
-        for exchange in ("nccl", "auto", "a2a"):
+        # SLM_TEST_EXCHANGES=auto restricts the exchanges (quick re-validation of one path)
+        for exchange in [x for x in os.environ.get("SLM_TEST_EXCHANGES", "").split(",") if x] or ("nccl", "auto", "a2a"):
             mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), exchange), nprocs=world, join=True)
             print("world", world, "exchange requested", exchange, "used", open(tmp_path / "exchange.txt").read())
             for r in range(world):
