@@ -7,8 +7,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <new>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "slm_internal.cuh"
@@ -90,6 +92,74 @@ static int pin_reserve(slm_ctx *ctx, size_t bytes)
         return slm_fail(SLM_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
     }
     ctx->pin_bytes = want;
+    return SLM_OK;
+}
+
+// ---- pageable host inputs --------------------------------------------------------------------------------------------
+// cudaMemcpyAsync from PAGEABLE memory is staged by the driver on the calling thread at ~11 GB/s (measured: config 5's
+// 320 MB train set, 29 ms per call against 6 ms from pinned memory) -- and the drop-in caller hands exactly such arrays
+// (numpy from ORB, orb.py:23-24).  So a long pageable train set is copied by a few host threads into a ring of pinned
+// chunks, each chunk going out over PCIe (and being searched) while the next ones are filled.
+#include "host_stager.h"
+
+static bool host_is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int stage_reserve(slm_ctx *ctx, size_t bytes)
+{
+    if (bytes > ctx->stage_bytes) {
+        if (ctx->stage_pin) {
+            SLM_CUDA(cudaDeviceSynchronize());
+            SLM_CUDA(cudaFreeHost(ctx->stage_pin));
+            ctx->stage_pin = nullptr;
+            ctx->stage_bytes = 0;
+        }
+        cudaError_t e = cudaMallocHost(&ctx->stage_pin, bytes);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            ctx->stage_pin = nullptr;
+            return slm_fail(SLM_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        ctx->stage_bytes = bytes;
+    }
+    for (cudaEvent_t &ev : ctx->stage_ev) {
+        if (!ev) SLM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        else SLM_CUDA(cudaEventSynchronize(ev));      // an earlier upload may still be reading the ring
+    }
+    return SLM_OK;
+}
+
+// One host array -> device on `stream`.  Pinned (or small) sources are handed to the driver as they are; a long pageable one
+// goes through the pinned ring in 8 MB pieces filled by the host threads.
+static int upload_host(slm_ctx *ctx, void *dst, const uint8_t *src, size_t bytes, cudaStream_t stream)
+{
+    const size_t kPiece = (size_t)8 << 20;
+    if (bytes == 0) return SLM_OK;
+    if (ctx->host_threads <= 0 || bytes < 2 * kPiece || !host_is_pageable(src)) {
+        SLM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return SLM_OK;
+    }
+    SLM_TRY(stage_reserve(ctx, (size_t)kStageSlots * kPiece));
+    HostStager stager;
+    if (stager.start(src, bytes, kPiece, reinterpret_cast<uint8_t *>(ctx->stage_pin), ctx->host_threads) != 0)
+        return slm_fail(SLM_ERR_NOMEM, "could not start the host staging threads");
+    for (int64_t c = 0; c < stager.n_chunks; ++c) {
+        if (c >= kStageSlots) {
+            SLM_CUDA(cudaEventSynchronize(ctx->stage_ev[c % kStageSlots]));
+            stager.release(c - kStageSlots + 1);
+        }
+        const uint8_t *piece = stager.wait(c);
+        const size_t c0 = (size_t)c * kPiece, len = std::min(kPiece, bytes - c0);
+        SLM_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(dst) + c0, piece, len, cudaMemcpyHostToDevice, stream));
+        SLM_CUDA(cudaEventRecord(ctx->stage_ev[c % kStageSlots], stream));
+    }
     return SLM_OK;
 }
 
@@ -205,6 +275,14 @@ int slm_create(int device, slm_ctx **ctx_out)
         if (v == 120 || v == 40) ctx->tc4_chunk = v;
     }
     ctx->no_pdl = getenv("SLM_NO_PDL") != nullptr;
+    {
+        const unsigned hw = std::thread::hardware_concurrency();
+        ctx->host_threads = hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 0;
+        if (const char *e = getenv("SLM_HOST_STAGE_THREADS")) {
+            int v = atoi(e);
+            if (v >= 0 && v <= 32) ctx->host_threads = v;
+        }
+    }
     ctx->tc4_timing = getenv("SLM_TC4_TIMING") != nullptr;
     ctx->exchange_max_blocks = 2ll * prop.multiProcessorCount;
     if (const char *e = getenv("SLM_EXCHANGE_MAX_BLOCKS")) {
@@ -247,10 +325,13 @@ int slm_destroy(slm_ctx *ctx)
     if (!ctx) return SLM_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    slm_buf *bufs[] = {&ctx->scratch, &ctx->keys, &ctx->rev, &ctx->misc, &ctx->io, &ctx->tickets};
+    slm_buf *bufs[] = {&ctx->scratch, &ctx->keys, &ctx->rev, &ctx->misc, &ctx->io, &ctx->tickets, &ctx->chi2_leaves};
     for (slm_buf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->stage_pin) cudaFreeHost(ctx->stage_pin);
+    for (cudaEvent_t ev : ctx->stage_ev)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->done_counter) cudaFree(ctx->done_counter);
     if (ctx->exchange_status) cudaFreeHost(ctx->exchange_status);
     if (ctx->last_ev) cudaEventDestroy(ctx->last_ev);
@@ -639,7 +720,7 @@ int slm_chi2_scan(slm_ctx *ctx, const int32_t *hist, const int32_t *db, int64_t 
                   int32_t *best_idx, double *best_val, void *stream)
 {
     SLM_TRY(check_ctx(ctx));
-    if (n_db < 0 || n_words < 1 || n_words > 12288) return slm_fail(SLM_ERR_INVALID, "bad size (n_db=%lld n_words=%d)",
+    if (n_db < 0 || n_words < 1 || n_words > kChi2MaxWords) return slm_fail(SLM_ERR_INVALID, "bad size (n_db=%lld n_words=%d)",
                                                                       (long long)n_db, n_words);
     if (n_db == 0) return SLM_OK;
     if (!hist || !db || !dist_out || !best_idx || !best_val) return slm_fail(SLM_ERR_INVALID, "NULL pointer argument");
@@ -708,7 +789,7 @@ int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t
     uint8_t *pin = reinterpret_cast<uint8_t *>(ctx->pin);
     SLM_CUDA(cudaEventSynchronize(ctx->ev[0]));  // a batched call may still be reading the pinned block
 
-    SLM_CUDA(cudaMemcpyAsync(q_dev, q_host, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    SLM_TRY(upload_host(ctx, q_dev, q_host, (size_t)nq * 32, s));
     // Large train sets: the H2D copy (PCIe) takes longer than the search, so it is cut into chunks on a second
     // stream and every chunk is searched as soon as it has landed -- chunk = shard: per-chunk packed top-2 keys
     // are merged by global index exactly like the cross-GPU path.  (Cross-check needs the whole train set
@@ -719,11 +800,28 @@ int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t
         SLM_TRY(slm_buf_reserve(ctx, &ctx->rev, (size_t)n_chunks * nq * 16));
         uint64_t *chunk_keys = reinterpret_cast<uint64_t *>(ctx->rev.p);
         if (!ctx->copy_stream) SLM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        // a pageable train set goes through the pinned ring, filled by host threads (see HostStager)
+        HostStager stager;
+        const bool staged = ctx->host_threads > 0 && host_is_pageable(t_host);
+        if (staged) {
+            SLM_TRY(stage_reserve(ctx, (size_t)kStageSlots * kChunkRows * 32));
+            if (stager.start(t_host, (size_t)nt * 32, (size_t)kChunkRows * 32, reinterpret_cast<uint8_t *>(ctx->stage_pin),
+                             ctx->host_threads) != 0)
+                return slm_fail(SLM_ERR_NOMEM, "could not start the host staging threads");
+        }
         for (int64_t c = 0; c < n_chunks; ++c) {
             const int64_t r0 = c * kChunkRows, rows = (nt - r0 < kChunkRows) ? nt - r0 : kChunkRows;
             if (!ctx->chunk_ev[c]) SLM_CUDA(cudaEventCreateWithFlags(&ctx->chunk_ev[c], cudaEventDisableTiming));
-            SLM_CUDA(cudaMemcpyAsync(t_dev + r0 * 8, t_host + r0 * 32, (size_t)rows * 32, cudaMemcpyHostToDevice,
-                                     ctx->copy_stream));
+            const uint8_t *src = t_host + r0 * 32;
+            if (staged) {
+                if (c >= kStageSlots) {          // the slot chunk c is written into was last read by the copy of chunk c - slots
+                    SLM_CUDA(cudaEventSynchronize(ctx->stage_ev[c % kStageSlots]));
+                    stager.release(c - kStageSlots + 1);
+                }
+                src = stager.wait(c);
+            }
+            SLM_CUDA(cudaMemcpyAsync(t_dev + r0 * 8, src, (size_t)rows * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (staged) SLM_CUDA(cudaEventRecord(ctx->stage_ev[c % kStageSlots], ctx->copy_stream));
             SLM_CUDA(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
             SLM_CUDA(cudaStreamWaitEvent(s, ctx->chunk_ev[c], 0));
             SLM_TRY(knn2_keys_dispatch(ctx, q_dev, nq, t_dev + r0 * 8, rows, r0, chunk_keys + c * nq * 2, s));
@@ -731,7 +829,7 @@ int slm_knn2_host(slm_ctx *ctx, const uint8_t *q_host, int64_t nq, const uint8_t
         SLM_TRY(slm_merge_finalize(ctx, chunk_keys, (int32_t)n_chunks, nq, ratio_num, ratio_den, idx_dev, dist_dev,
                                    accept_out ? acc_dev : nullptr, s));
     } else {
-        if (nt > 0) SLM_CUDA(cudaMemcpyAsync(t_dev, t_host, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+        SLM_TRY(upload_host(ctx, t_dev, t_host, (size_t)nt * 32, s));
         SLM_TRY(slm_knn2_filter(ctx, q_dev, nq, t_dev, nt, 0, ratio_num, ratio_den, cross_check, idx_dev, dist_dev,
                                 accept_out ? acc_dev : nullptr, s));
     }

@@ -10,6 +10,8 @@
 // The scan is the one HBM-bound loop of the pipeline (4*k bytes per stored keyframe, no reuse).
 // Results are BIT-exact with numpy: the terms are IEEE double divisions of exactly representable integers
 // and the sum follows numpy's pairwise_sum order (8 accumulators for n <= 128, recursive halves above).
+#include <atomic>
+#include <vector>
 #include "slm_internal.cuh"
 
 namespace {
@@ -77,6 +79,37 @@ __global__ void chi2_scan_kernel(const int *hq, const int *db, long long n_db, i
     if (i < n_db) dist[i] = pairwise_chi2(shq, db + i * k, k);
 }
 
+// Large vocabularies (k > 12288: the query histogram no longer fits 48 KB of shared memory, and one thread per stored
+// histogram would walk a 4 * k-byte row alone): ONE BLOCK per stored histogram.  numpy's pairwise sum is a binary tree whose
+// leaves are runs of <= 128 elements (8 accumulators each) -- the leaves (offset, length; computed on the host for this k)
+// are summed by the threads in parallel, every thread reading whole 128-byte lines of its runs, and thread 0 then adds the
+// leaf sums in the recursion's own order, so the result is still bit-identical with np.sum.
+__device__ double chi2_tree(int n, const double *leaf_sum, int &next)
+{
+    if (n <= 128) return leaf_sum[next++];
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const double a = chi2_tree(n2, leaf_sum, next);
+    const double b = chi2_tree(n - n2, leaf_sum, next);
+    return __dadd_rn(a, b);
+}
+
+__global__ void __launch_bounds__(128) chi2_scan_wide_kernel(const int *hq, const int *db, long long n_db, int k,
+                                                             const int2 *leaves, int n_leaves, double *dist)
+{
+    extern __shared__ double leaf_sum[];
+    const int *row = db + (long long)blockIdx.x * k;
+    for (int l = threadIdx.x; l < n_leaves; l += blockDim.x) {
+        const int2 lf = leaves[l];
+        leaf_sum[l] = pairwise_chi2(hq + lf.x, row + lf.x, lf.y);       // lf.y <= 128: the non-recursive branches
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int next = 0;
+        dist[blockIdx.x] = chi2_tree(k, leaf_sum, next);
+    }
+}
+
 // np.argmin / np.min: first index of the smallest value.  One CTA.
 __global__ void argmin_kernel(const double *dist, long long n, int *best_idx, double *best_val)
 {
@@ -128,7 +161,37 @@ int slm_chi2_scan_impl(slm_ctx *ctx, const int32_t *hq, const int32_t *db, int64
                        int32_t *best_idx, double *best_val, cudaStream_t stream)
 {
     if (n_db <= 0) return SLM_OK;
-    chi2_scan_kernel<<<(unsigned)((n_db + 127) / 128), 128, (size_t)k * sizeof(int), stream>>>(hq, db, n_db, k, dist);
+    if (k > kChi2SmemWords) {
+        // leaves of numpy's pairwise-sum tree for this k (cached on the ctx while k stays the same)
+        if (ctx->chi2_leaves_k != k) {
+            std::vector<int2> lv;
+            std::vector<int2> stack{make_int2(0, k)};
+            while (!stack.empty()) {                         // depth-first, left child first = the recursion's leaf order
+                const int2 r = stack.back();
+                stack.pop_back();
+                if (r.y <= 128) { lv.push_back(r); continue; }
+                int n2 = r.y / 2;
+                n2 -= n2 % 8;
+                stack.push_back(make_int2(r.x + n2, r.y - n2));
+                stack.push_back(make_int2(r.x, n2));
+            }
+            SLM_TRY(slm_buf_reserve(ctx, &ctx->chi2_leaves, lv.size() * sizeof(int2)));
+            // pageable source: the driver has staged it when the call returns, so `lv` may go out of scope
+            SLM_CUDA(cudaMemcpyAsync(ctx->chi2_leaves.p, lv.data(), lv.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
+            ctx->chi2_leaves_k = k;
+            ctx->chi2_n_leaves = (int)lv.size();
+        }
+        const size_t smem = (size_t)ctx->chi2_n_leaves * sizeof(double);
+        static std::atomic<bool> configured[64];
+        if (smem > 48 * 1024 && !configured[ctx->device & 63].load()) {
+            SLM_CUDA(cudaFuncSetAttribute(chi2_scan_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured[ctx->device & 63].store(true);
+        }
+        chi2_scan_wide_kernel<<<(unsigned)n_db, 128, smem, stream>>>(hq, db, n_db, k, reinterpret_cast<const int2 *>(ctx->chi2_leaves.p),
+                                                                    ctx->chi2_n_leaves, dist);
+    } else {
+        chi2_scan_kernel<<<(unsigned)((n_db + 127) / 128), 128, (size_t)k * sizeof(int), stream>>>(hq, db, n_db, k, dist);
+    }
     SLM_CUDA(cudaGetLastError());
     argmin_kernel<<<1, 1024, 0, stream>>>(dist, n_db, best_idx, best_val);
     SLM_CUDA(cudaGetLastError());

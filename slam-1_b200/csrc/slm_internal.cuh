@@ -40,9 +40,16 @@ struct slm_ctx {
     slm_buf misc;      // pair lists, expanded operands, ...
     slm_buf io;        // device copies of host inputs / outputs (slm_knn2_host)
     slm_buf tickets;   // per-group atomic tickets of the frame kernel (zero between launches)
+    slm_buf chi2_leaves;   // leaves of numpy's pairwise-sum tree for chi2_leaves_k words (wide chi-square scan, bow.cu)
+    int chi2_leaves_k = 0, chi2_n_leaves = 0;
     // pinned staging for host results
     void *pin = nullptr;
     size_t pin_bytes = 0;
+    // pinned ring the host path stages PAGEABLE train sets through (kStageSlots chunks), filled by host_threads threads
+    void *stage_pin = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t stage_ev[4] = {};                 // H2D of the chunk in slot i has finished: the slot may be refilled
+    int host_threads = 4;                         // SLM_HOST_STAGE_THREADS (0 = let the driver stage pageable memory)
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;           // H2D chunks of slm_knn2_host
     cudaEvent_t chunk_ev[kMaxHostChunks] = {};
@@ -235,6 +242,10 @@ int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
 int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
                           int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain = nullptr);
 
+// chi-square scan: up to this many words the query histogram is staged in shared memory (one thread per stored histogram);
+// above, one block per stored histogram (chi2_scan_wide_kernel).  Largest supported vocabulary: kChi2MaxWords.
+static constexpr int kChi2SmemWords = 12288;
+static constexpr int kChi2MaxWords = 1 << 20;
 // ---- bag-of-words follow-on (bow.cu) ------------------------------------------------------------------
 int slm_bow_hist_impl(slm_ctx *ctx, const int32_t *idx, int64_t n, int32_t idx_stride, int32_t n_words, int32_t *hist,
                       cudaStream_t stream);

@@ -9,10 +9,10 @@ libslammatch.so (hand-written CUDA for sm_100a behind the C-ABI of include/slamm
 from . import synth  # noqa: F401  (pure numpy; safe without a GPU)
 from ._lib import SlamMatchError, Context, context, load, LIB_PATH, SYMBOLS, VARIANTS  # noqa: F401
 from .matcher import (DMatch, Matcher, REFERENCE_RATIO, find_2d_3d_device, get_matches, get_matches_device,  # noqa: F401
-                      good_matches, install, knn2, stereo_matches_device, uninstall)
+                      good_matches, install, knn2, knn2_batched, stereo_matches_device, uninstall)
 
 from .keyframe_db import KeyframeDB, ShardedKeyframeDB  # noqa: F401,E402
 
-__all__ = ["KeyframeDB", "ShardedKeyframeDB", "Matcher", "DMatch", "knn2", "install", "uninstall", "get_matches",
+__all__ = ["KeyframeDB", "ShardedKeyframeDB", "Matcher", "DMatch", "knn2", "knn2_batched", "install", "uninstall", "get_matches",
            "get_matches_device", "find_2d_3d_device", "stereo_matches_device", "good_matches", "context",
            "Context", "SlamMatchError", "load", "synth", "REFERENCE_RATIO"]

@@ -205,6 +205,57 @@ def _knn2_masked(q, t, mask, num, den, device, base):
     return idx.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy()
 
 
+def knn2_batched(desc, pairs, ratio=REFERENCE_RATIO, out=None, device: int | None = None, variant: str | None = None):
+    """Many frame-to-frame problems in one call (BASELINE config 3: the local-mapping batch -- every keyframe pair of a window
+    matched with the arithmetic of tracking.py:22-30): ``desc`` is ``uint8[n_frames, n, 32]``, ``pairs`` is
+    ``int32[n_pairs, 2]`` of (query frame, train frame).  Returns ``idx int32[n_pairs, n, 2]`` (train rows local to the train
+    frame), ``dist int32[n_pairs, n, 2]``, ``accept uint8[n_pairs, n]``.
+
+    CUDA tensors in -> CUDA tensors out.  Host arrays (numpy, or CPU tensors -- pinned ones are copied asynchronously) in ->
+    numpy arrays out; ``out=(idx, dist, accept)`` names preallocated host buffers (numpy arrays or CPU tensors, ideally
+    pinned and reused from call to call: a fresh pageable 68 MB result costs more than the search of config 3 itself).
+    """
+    import torch
+    num, den = _ratio_args(ratio)
+    pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32))
+    if pairs.ndim != 2 or pairs.shape[1] != 2:
+        raise ValueError(f"pairs: expected int32[n_pairs, 2], got {pairs.shape}")
+    on_device = _is_torch_cuda(desc)
+    d = desc if on_device or isinstance(desc, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(desc))
+    if d.dim() != 3 or not ((d.dtype == torch.uint8 and d.shape[2] == 32) or (d.dtype == torch.int32 and d.shape[2] == 8)):
+        raise ValueError(f"desc: expected uint8[n_frames, n, 32], got {d.dtype} {tuple(d.shape)}")
+    n_frames, n = int(d.shape[0]), int(d.shape[1])
+    if pairs.size and (pairs.min() < 0 or pairs.max() >= n_frames):
+        raise ValueError("pairs: frame index out of range")
+    dev = d.device if on_device else torch.device("cuda", 0 if device is None else device)
+    if not on_device and not torch.cuda.is_available():
+        raise _lib.SlamMatchError(-2, "CUDA device required: there is no CPU path")
+    dd = d.contiguous() if on_device else d.contiguous().to(dev, non_blocking=True)
+    ctx = _lib.context(dev.index or 0)
+    P = pairs.shape[0]
+    idx = torch.empty((P, n, 2), dtype=torch.int32, device=dev)
+    dist = torch.empty((P, n, 2), dtype=torch.int32, device=dev)
+    acc = torch.empty((P, n), dtype=torch.uint8, device=dev)
+    if P and n:
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with ctx.using(variant):
+            _lib.check(ctx.lib.slm_knn2_batched(ctx.handle, dd.data_ptr(), n_frames, n, pairs.ctypes.data, P, num, den,
+                                                idx.data_ptr(), dist.data_ptr(), acc.data_ptr(), stream))
+    if on_device:
+        return idx, dist, acc
+    if out is None:
+        return idx.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy()
+    res = []
+    for o, src in zip(out, (idx, dist, acc)):
+        ot = o if isinstance(o, torch.Tensor) else torch.from_numpy(o)
+        if tuple(ot.shape) != tuple(src.shape) or ot.dtype != src.dtype or not ot.is_contiguous():
+            raise ValueError(f"out: expected contiguous {src.dtype} {tuple(src.shape)}, got {ot.dtype} {tuple(ot.shape)}")
+        ot.copy_(src, non_blocking=True)
+        res.append(ot.numpy())
+    torch.cuda.current_stream(dev).synchronize()
+    return tuple(res)
+
+
 class Matcher:
     """Drop-in for the object built by ``cv2.FlannBasedMatcher(indexParams=..., searchParams=...)``.
 

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+import slammatch
 from slammatch import _lib, synth
 from oracle import oracle as orc
 
@@ -115,3 +116,44 @@ def test_frame_refine_kernel_many_pairs(n, variant):
         else:
             for x, y in zip(ref, out):
                 assert np.array_equal(x, y), env
+
+
+def test_public_knn2_batched_host_device_and_out_buffers():
+    """slammatch.knn2_batched (the public call of config 3): numpy in / numpy out, pinned CPU tensors in with caller-owned
+    pinned result buffers, CUDA tensors in / out -- all equal to the oracle pair by pair; argument errors are ValueErrors."""
+    import torch
+    frames, n = 5, 700
+    rng = np.random.default_rng(11)
+    base = synth.uniform(n, 60)
+    desc = np.stack([base ^ np.packbits(rng.random((n, 256)) < 0.04 * (f + 1), axis=1, bitorder="little") for f in range(frames)])
+    pairs = np.array([(i, j) for i in range(frames) for j in range(frames) if i != j], dtype=np.int32)   # ordered pairs
+    P = pairs.shape[0]
+    want = [orc.c_knn2(desc[a], desc[b]) for a, b in pairs]
+
+    def check(idx, dist, acc):
+        for p in range(P):
+            oi, od = want[p]
+            assert np.array_equal(idx[p], oi) and np.array_equal(dist[p], od), p
+            assert np.array_equal(acc[p], orc.c_ratio(od, 7, 10)), p
+
+    check(*slammatch.knn2_batched(desc, pairs))
+    out = (torch.empty((P, n, 2), dtype=torch.int32).pin_memory(), torch.empty((P, n, 2), dtype=torch.int32).pin_memory(),
+           torch.empty((P, n), dtype=torch.uint8).pin_memory())
+    for _ in range(2):
+        res = slammatch.knn2_batched(torch.from_numpy(desc).pin_memory(), pairs, ratio=(7, 10), out=out)
+        check(*res)
+        assert res[0].ctypes.data == out[0].data_ptr()          # written in place
+    out_np = (np.empty((P, n, 2), np.int32), np.empty((P, n, 2), np.int32), np.empty((P, n), np.uint8))
+    check(*slammatch.knn2_batched(desc, pairs, out=out_np))
+    check(*out_np)
+    di, dd_, da = slammatch.knn2_batched(torch.from_numpy(desc).cuda(), pairs)
+    assert di.is_cuda
+    check(di.cpu().numpy(), dd_.cpu().numpy(), da.cpu().numpy())
+    i0, d0, a0 = slammatch.knn2_batched(desc, np.zeros((0, 2), np.int32))
+    assert i0.shape == (0, n, 2) and a0.shape == (0, n)
+    with pytest.raises(ValueError):
+        slammatch.knn2_batched(desc, np.array([[0, frames]], np.int32))
+    with pytest.raises(ValueError):
+        slammatch.knn2_batched(desc[:, :, :16], pairs)
+    with pytest.raises(ValueError):
+        slammatch.knn2_batched(desc, pairs, out=(out_np[0], out_np[1], np.empty((P, n + 1), np.uint8)))

@@ -67,6 +67,51 @@ def test_chi2_scan_first_minimum_wins_and_sum_order_is_numpys():
         assert int(bi.item()) == int(np.argmin(want)) == 20 and float(bv.item()) == float(np.min(want))
 
 
+@pytest.mark.gpu
+def test_chi2_scan_wide_vocabularies_are_bit_exact_too():
+    """Above 12288 words (config 4's 65 536-word vocabulary) the scan takes one block per stored histogram: the leaves of
+    numpy's pairwise-sum tree in parallel, then the tree itself -- still every distance bit-identical with np.sum; k changes
+    between calls (the cached leaf table is rebuilt), an odd k and a k with > 6144 leaves (> 48 KB of leaf sums)."""
+    import torch
+    from slammatch import _lib
+    ctx = _lib.context(0)
+    rng = np.random.default_rng(10)
+    for k, n_db in ((12289, 40), (65536, 60), (65536, 7), (100003, 12), (12288, 30), (500000, 3)):
+        db = rng.integers(0, 6, (n_db, k)).astype(np.int32)
+        db[n_db - 1] = db[1]                                   # exact tie: argmin must report 1
+        h = db[1].copy(); h[::977] += 2
+        want = np.array([orc.np_chi2(h.astype(np.int64), r.astype(np.int64)) for r in db])
+        hd, dd = torch.from_numpy(h).cuda(), torch.from_numpy(db).cuda()
+        dist = torch.empty(n_db, dtype=torch.float64, device="cuda")
+        bi = torch.empty(1, dtype=torch.int32, device="cuda"); bv = torch.empty(1, dtype=torch.float64, device="cuda")
+        _lib.check(ctx.lib.slm_chi2_scan(ctx.handle, hd.data_ptr(), dd.data_ptr(), n_db, k, dist.data_ptr(),
+                                         bi.data_ptr(), bv.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(dist.cpu().numpy(), want), k
+        assert int(bi.item()) == int(np.argmin(want)) == 1 and float(bv.item()) == float(np.min(want))
+    assert ctx.lib.slm_chi2_scan(ctx.handle, hd.data_ptr(), dd.data_ptr(), 1, (1 << 20) + 1, dist.data_ptr(), bi.data_ptr(),
+                                 bv.data_ptr(), None) == -1
+
+
+@pytest.mark.gpu
+def test_bow_predict_with_a_64k_word_vocabulary():
+    """BoW.predict / predict_previous at config 4's vocabulary size (was rejected: > 12288 words)."""
+    from slammatch.bow import BoW
+    k, n_img, n_desc = 65536, 9, 2000
+    vocab = synth.uniform(k, 31)
+    imgs = [synth.planted(n_desc, k, 500 + i)[0] for i in range(n_img)]
+    bow = BoW(vocab, capacity=4)
+    bow.train(imgs)
+    db = bow.db
+    q = synth.planted(n_desc, k, 600)[0]
+    h = orc.np_bow_hist(orc.c_knn2(q, vocab)[0][:, 0], k)
+    assert np.array_equal(bow.hist(q), h)
+    want = orc.np_predict_previous(h, db, n_img - 1, 2)
+    assert bow.predict_previous(q, n_img - 1, 2) == want
+    i, v = bow.predict(imgs[4])
+    assert (i, v) == (4, 0.0)
+
+
 def test_vocab_update_rule_majority_ties_and_empty_words():
     """The k-majority update rule of the oracle itself on a hand-made case (CPU only)."""
     desc = np.zeros((5, 32), np.uint8)
