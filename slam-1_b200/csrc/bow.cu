@@ -79,19 +79,49 @@ __global__ void chi2_scan_kernel(const int *hq, const int *db, long long n_db, i
     if (i < n_db) dist[i] = pairwise_chi2(shq, db + i * k, k);
 }
 
-// Large vocabularies (k > 12288: the query histogram no longer fits 48 KB of shared memory, and one thread per stored
-// histogram would walk a 4 * k-byte row alone): ONE BLOCK per stored histogram.  numpy's pairwise sum is a binary tree whose
+// Larger vocabularies (k > kChi2SmemWords: one thread per stored histogram would walk a 4 * k-byte row alone, and the
+// recursive pairwise_chi2 above would outgrow the 1 KB per-thread stack beyond 8192 words -- a latent fault of the first
+// version of this scan, which accepted 12288): ONE BLOCK per stored histogram.  numpy's pairwise sum is a binary tree whose
 // leaves are runs of <= 128 elements (8 accumulators each) -- the leaves (offset, length; computed on the host for this k)
 // are summed by the threads in parallel, every thread reading whole 128-byte lines of its runs, and thread 0 then adds the
 // leaf sums in the recursion's own order, so the result is still bit-identical with np.sum.
-__device__ double chi2_tree(int n, const double *leaf_sum, int &next)
+// The recursion  sum(n) = sum(n2) + sum(n - n2),  n2 = n / 2 rounded down to a multiple of 8,  over the leaf sums in leaf
+// order -- written as a loop with an explicit stack (depth <= 14 for 2^20 words): device recursion would live on the
+// 1 KB default per-thread stack.
+__device__ double chi2_tree(int k, const double *leaf_sum)
 {
-    if (n <= 128) return leaf_sum[next++];
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    const double a = chi2_tree(n2, leaf_sum, next);
-    const double b = chi2_tree(n - n2, leaf_sum, next);
-    return __dadd_rn(a, b);
+    int n_of[24];
+    double left_of[24];
+    bool has_left[24];
+    int sp = 0, next = 0;
+    n_of[0] = k;
+    has_left[0] = false;
+    double ret = 0.0;
+    bool returning = false;
+    while (sp >= 0) {
+        const int n = n_of[sp];
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        if (!returning) {
+            if (n <= 128) {                      // a leaf: return its sum to the parent
+                ret = leaf_sum[next++];
+                returning = true;
+                --sp;
+            } else {                             // descend into the left child
+                has_left[sp] = false;
+                n_of[++sp] = n2;
+            }
+        } else if (!has_left[sp]) {              // back from the left child: keep it, descend into the right child
+            left_of[sp] = ret;
+            has_left[sp] = true;
+            returning = false;
+            n_of[++sp] = n - n2;
+        } else {                                 // back from the right child
+            ret = __dadd_rn(left_of[sp], ret);
+            --sp;
+        }
+    }
+    return ret;
 }
 
 __global__ void __launch_bounds__(128) chi2_scan_wide_kernel(const int *hq, const int *db, long long n_db, int k,
@@ -104,10 +134,7 @@ __global__ void __launch_bounds__(128) chi2_scan_wide_kernel(const int *hq, cons
         leaf_sum[l] = pairwise_chi2(hq + lf.x, row + lf.x, lf.y);       // lf.y <= 128: the non-recursive branches
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int next = 0;
-        dist[blockIdx.x] = chi2_tree(k, leaf_sum, next);
-    }
+    if (threadIdx.x == 0) dist[blockIdx.x] = chi2_tree(k, leaf_sum);
 }
 
 // np.argmin / np.min: first index of the smallest value.  One CTA.

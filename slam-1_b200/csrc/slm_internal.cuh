@@ -242,9 +242,10 @@ int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
 int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
                           int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain = nullptr);
 
-// chi-square scan: up to this many words the query histogram is staged in shared memory (one thread per stored histogram);
-// above, one block per stored histogram (chi2_scan_wide_kernel).  Largest supported vocabulary: kChi2MaxWords.
-static constexpr int kChi2SmemWords = 12288;
+// chi-square scan: up to this many words one thread scans one stored histogram (query histogram in shared memory; the
+// recursive pairwise sum is then at most 4 frames = 576 bytes deep); above, one block per stored histogram
+// (chi2_scan_wide_kernel).  Largest supported vocabulary: kChi2MaxWords.
+static constexpr int kChi2SmemWords = 1024;
 static constexpr int kChi2MaxWords = 1 << 20;
 // ---- bag-of-words follow-on (bow.cu) ------------------------------------------------------------------
 int slm_bow_hist_impl(slm_ctx *ctx, const int32_t *idx, int64_t n, int32_t idx_stride, int32_t n_words, int32_t *hist,

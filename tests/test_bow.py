@@ -69,14 +69,16 @@ def test_chi2_scan_first_minimum_wins_and_sum_order_is_numpys():
 
 @pytest.mark.gpu
 def test_chi2_scan_wide_vocabularies_are_bit_exact_too():
-    """Above 12288 words (config 4's 65 536-word vocabulary) the scan takes one block per stored histogram: the leaves of
+    """Above 1024 words (config 4's vocabulary has 65 536) the scan takes one block per stored histogram: the leaves of
     numpy's pairwise-sum tree in parallel, then the tree itself -- still every distance bit-identical with np.sum; k changes
-    between calls (the cached leaf table is rebuilt), an odd k and a k with > 6144 leaves (> 48 KB of leaf sums)."""
+    between calls (the cached leaf table is rebuilt), odd sizes, and the sizes between 8192 and 12288 words at which the
+    first version of the scan (one thread per histogram, recursive sum) outgrew the per-thread stack."""
     import torch
     from slammatch import _lib
     ctx = _lib.context(0)
     rng = np.random.default_rng(10)
-    for k, n_db in ((12289, 40), (65536, 60), (65536, 7), (100003, 12), (12288, 30), (500000, 3)):
+    for k, n_db in ((1024, 300), (1025, 50), (4099, 30), (12288, 30), (12289, 40), (65536, 60), (65536, 7), (100003, 12),
+                    (1024, 5), (500000, 3)):
         db = rng.integers(0, 6, (n_db, k)).astype(np.int32)
         db[n_db - 1] = db[1]                                   # exact tie: argmin must report 1
         h = db[1].copy(); h[::977] += 2

@@ -47,7 +47,6 @@ def test_pageable_long_train_set_through_the_staging_ring():
             for _ in range(2):                                   # the ring and its events are reused from call to call
                 i, d, a = _host_call(ctx, q, t)
                 assert np.array_equal(i, oi) and np.array_equal(d, od) and np.array_equal(a, want), threads
-            assert ctx.last_kernel() == "knn2_tc4_kernel"
         finally:
             ctx.close()
     # pinned inputs take the direct path
