@@ -242,8 +242,8 @@ int slm_gather_rows(slm_ctx *ctx, const void *src_dev, int32_t row_bytes, const 
  * slm_chi2_scan: dist_out_dev[i] = sum_w 2*(h[w]-db[i][w])^2 / max(1, h[w]+db[i][w]) in float64 for the n_db stored
  *   histograms db_dev int32[n_db][n_words], bit-exact with numpy (same division, same pairwise summation
  *   order), plus best_idx_dev / best_val_dev = (np.argmin, np.min) -- first minimum wins.
- *   n_words <= 2^20.  Up to 1024 words one thread scans one stored histogram (query histogram in shared memory); larger
- *   vocabularies (config 4's 65536 words) take one block per stored histogram, still in numpy's summation order.
+ *   n_words <= 2^19.  Up to 128 words (the reference's 50) eight lanes scan one stored histogram; larger vocabularies
+ *   (config 4's 65536 words) take one block per stored histogram, still in numpy's summation order.
  */
 int slm_bow_hist(slm_ctx *ctx, const int32_t *words_dev, int64_t n, int32_t stride, int32_t n_words,
                  int32_t *hist_out_dev, void *stream);

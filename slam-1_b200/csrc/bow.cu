@@ -9,10 +9,14 @@
 //   scan  :38-42   dist over db[0 : i+1-threshold]; (np.argmin(dist), np.min(dist))
 // The scan is the one HBM-bound loop of the pipeline (4*k bytes per stored keyframe, no reuse).
 // Results are BIT-exact with numpy: the terms are IEEE double divisions of exactly representable integers
-// and the sum follows numpy's pairwise_sum order (8 accumulators for n <= 128, recursive halves above).
+// and the sum follows numpy's pairwise_sum order (8 accumulators for n <= 128, a binary tree of such leaves above).
+#include <algorithm>
 #include <atomic>
+#include <cstring>
+#include <numeric>
 #include <vector>
 #include "slm_internal.cuh"
+#include "chi2_plan.h"
 
 namespace {
 
@@ -43,98 +47,74 @@ __device__ __forceinline__ double chi2_term(int x, int y)
     return __ddiv_rn((double)num, (double)den);      // true divide: both converted to float64
 }
 
-// numpy's pairwise_sum for a contiguous float64 vector whose i-th element is chi2_term(hq[i], row[i]).
-__device__ double pairwise_chi2(const int *hq, const int *row, int n)
+// numpy's pairwise_sum of the float64 vector whose i-th element is chi2_term(hq[i], row[i]):
+//   n < 8     sequential;
+//   n <= 128  ("leaf") eight accumulators r[j] += a[i + j] for i = 0, 8, 16, ...; ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); the
+//             n % 8 trailing elements are added one by one;
+//   n > 128   sum(first n2) + sum(rest), n2 = n / 2 rounded down to a multiple of 8 -- a binary tree over leaves.
+// A leaf is summed by an 8-LANE GROUP, lane j owning accumulator r[j]: every step of a group reads 8 consecutive words of
+// the stored histogram (one 32-byte sector) and of the query histogram, so a warp request covers four full sectors instead
+// of 32 scattered words (one thread per stored histogram -- the first version of this scan -- reached 4 % of the HBM
+// bandwidth and needed device recursion); the three XOR-shuffle additions reproduce the association above exactly
+// (IEEE addition is commutative, so lane 1's r1 + r0 is lane 0's r0 + r1).  The result is valid in every lane of the group.
+__device__ __forceinline__ double chi2_leaf8(const int *hq, const int *row, int n, int j, unsigned group_mask)
 {
+    double r = 0.0;
     if (n < 8) {
-        double r = 0.0;
-        for (int i = 0; i < n; ++i) r = __dadd_rn(r, chi2_term(hq[i], row[i]));
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, chi2_term(__ldg(hq + i), __ldg(row + i)));
         return r;
     }
-    if (n <= 128) {
-        double r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = chi2_term(hq[j], row[j]);
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], chi2_term(hq[i + j], row[i + j]));
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, chi2_term(hq[i], row[i]));
-        return res;
-    }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(pairwise_chi2(hq, row, n2), pairwise_chi2(hq + n2, row + n2, n - n2));
+    const int n8 = n - (n % 8);
+    r = chi2_term(__ldg(hq + j), __ldg(row + j));
+    for (int i = 8; i < n8; i += 8) r = __dadd_rn(r, chi2_term(__ldg(hq + i + j), __ldg(row + i + j)));
+    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 4));
+    for (int i = n8; i < n; ++i) r = __dadd_rn(r, chi2_term(__ldg(hq + i), __ldg(row + i)));
+    return r;
 }
 
-__global__ void chi2_scan_kernel(const int *hq, const int *db, long long n_db, int k, double *dist)
+// k <= 128 words (the reference's 50-bin histograms): the whole histogram is one leaf -- one 8-lane group per stored
+// histogram, 16 stored histograms per block.
+__global__ void __launch_bounds__(128) chi2_scan_kernel(const int *hq, const int *db, long long n_db, int k, double *dist)
 {
-    extern __shared__ int shq[];
-    for (int w = threadIdx.x; w < k; w += blockDim.x) shq[w] = hq[w];
-    __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_db) dist[i] = pairwise_chi2(shq, db + i * k, k);
+    const int j = threadIdx.x & 7;
+    const unsigned group_mask = 0xFFu << (threadIdx.x & 24);
+    const long long i = (long long)blockIdx.x * 16 + (threadIdx.x >> 3);
+    if (i >= n_db) return;                               // whole groups leave
+    const double r = chi2_leaf8(hq, db + i * k, k, j, group_mask);
+    if (j == 0) dist[i] = r;
 }
 
-// Larger vocabularies (k > kChi2SmemWords: one thread per stored histogram would walk a 4 * k-byte row alone, and the
-// recursive pairwise_chi2 above would outgrow the 1 KB per-thread stack beyond 8192 words -- a latent fault of the first
-// version of this scan, which accepted 12288): ONE BLOCK per stored histogram.  numpy's pairwise sum is a binary tree whose
-// leaves are runs of <= 128 elements (8 accumulators each) -- the leaves (offset, length; computed on the host for this k)
-// are summed by the threads in parallel, every thread reading whole 128-byte lines of its runs, and thread 0 then adds the
-// leaf sums in the recursion's own order, so the result is still bit-identical with np.sum.
-// The recursion  sum(n) = sum(n2) + sum(n - n2),  n2 = n / 2 rounded down to a multiple of 8,  over the leaf sums in leaf
-// order -- written as a loop with an explicit stack (depth <= 14 for 2^20 words): device recursion would live on the
-// 1 KB default per-thread stack.
-__device__ double chi2_tree(int k, const double *leaf_sum)
-{
-    int n_of[24];
-    double left_of[24];
-    bool has_left[24];
-    int sp = 0, next = 0;
-    n_of[0] = k;
-    has_left[0] = false;
-    double ret = 0.0;
-    bool returning = false;
-    while (sp >= 0) {
-        const int n = n_of[sp];
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        if (!returning) {
-            if (n <= 128) {                      // a leaf: return its sum to the parent
-                ret = leaf_sum[next++];
-                returning = true;
-                --sp;
-            } else {                             // descend into the left child
-                has_left[sp] = false;
-                n_of[++sp] = n2;
-            }
-        } else if (!has_left[sp]) {              // back from the left child: keep it, descend into the right child
-            left_of[sp] = ret;
-            has_left[sp] = true;
-            returning = false;
-            n_of[++sp] = n - n2;
-        } else {                                 // back from the right child
-            ret = __dadd_rn(left_of[sp], ret);
-            --sp;
-        }
-    }
-    return ret;
-}
+// k > 128 words (config 4's vocabulary has 65 536): ONE BLOCK per stored histogram.  The leaves (offset, length) and the
+// inner nodes of the recursion  sum(n) = sum(n2) + sum(n - n2)  are laid out on the host for this k: value slots
+// [0, n_leaves) are the leaf sums, slot n_leaves + i is inner node i = slot[left] + slot[right] (left operand first, as the
+// recursion adds them), inner nodes sorted by height so that every level only reads finished slots.  The block's sixteen
+// 8-lane groups sum the leaves, then the levels are added in parallel (9 levels for 65 536 words; a single thread walking
+// the tree was most of the first wide kernel's time).  Bit-identical with np.sum.
 
 __global__ void __launch_bounds__(128) chi2_scan_wide_kernel(const int *hq, const int *db, long long n_db, int k,
-                                                             const int2 *leaves, int n_leaves, double *dist)
+                                                             const int2 *leaves, int n_leaves, const int2 *nodes,
+                                                             Chi2Levels lv, double *dist)
 {
-    extern __shared__ double leaf_sum[];
+    extern __shared__ double slot[];
+    const int j = threadIdx.x & 7, group = threadIdx.x >> 3;
+    const unsigned group_mask = 0xFFu << (threadIdx.x & 24);
     const int *row = db + (long long)blockIdx.x * k;
-    for (int l = threadIdx.x; l < n_leaves; l += blockDim.x) {
+    for (int l = group; l < n_leaves; l += 16) {
         const int2 lf = leaves[l];
-        leaf_sum[l] = pairwise_chi2(hq + lf.x, row + lf.x, lf.y);       // lf.y <= 128: the non-recursive branches
+        const double r = chi2_leaf8(hq + lf.x, row + lf.x, lf.y, j, group_mask);
+        if (j == 0) slot[l] = r;
+    }
+    for (int h = 0; h < lv.n_levels; ++h) {
+        __syncthreads();
+        for (int i = lv.start[h] + threadIdx.x; i < lv.start[h + 1]; i += blockDim.x) {
+            const int2 c = nodes[i];
+            slot[n_leaves + i] = __dadd_rn(slot[c.x], slot[c.y]);
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0) dist[blockIdx.x] = chi2_tree(k, leaf_sum);
+    if (threadIdx.x == 0) dist[blockIdx.x] = slot[n_leaves + lv.start[lv.n_levels] - 1];      // the root is the last inner node
 }
 
 // np.argmin / np.min: first index of the smallest value.  One CTA.
@@ -188,36 +168,35 @@ int slm_chi2_scan_impl(slm_ctx *ctx, const int32_t *hq, const int32_t *db, int64
                        int32_t *best_idx, double *best_val, cudaStream_t stream)
 {
     if (n_db <= 0) return SLM_OK;
-    if (k > kChi2SmemWords) {
-        // leaves of numpy's pairwise-sum tree for this k (cached on the ctx while k stays the same)
+    if (k > kChi2LeafWords) {
+        // leaves and inner nodes of numpy's pairwise-sum tree for this k (chi2_plan.h; cached on the ctx while k stays the same)
         if (ctx->chi2_leaves_k != k) {
-            std::vector<int2> lv;
-            std::vector<int2> stack{make_int2(0, k)};
-            while (!stack.empty()) {                         // depth-first, left child first = the recursion's leaf order
-                const int2 r = stack.back();
-                stack.pop_back();
-                if (r.y <= 128) { lv.push_back(r); continue; }
-                int n2 = r.y / 2;
-                n2 -= n2 % 8;
-                stack.push_back(make_int2(r.x + n2, r.y - n2));
-                stack.push_back(make_int2(r.x, n2));
-            }
-            SLM_TRY(slm_buf_reserve(ctx, &ctx->chi2_leaves, lv.size() * sizeof(int2)));
-            // pageable source: the driver has staged it when the call returns, so `lv` may go out of scope
-            SLM_CUDA(cudaMemcpyAsync(ctx->chi2_leaves.p, lv.data(), lv.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
+            const Chi2Plan plan = chi2_plan(k);
+            if (!plan.ok) return slm_fail(SLM_ERR_UNSUPPORTED, "chi-square scan: vocabulary too large (%d words)", k);
+            SLM_TRY(slm_buf_reserve(ctx, &ctx->chi2_leaves, plan.table.size() * sizeof(Chi2Pair)));
+            // pageable source: the driver has staged it when the call returns, so `plan` may go out of scope
+            SLM_CUDA(cudaMemcpyAsync(ctx->chi2_leaves.p, plan.table.data(), plan.table.size() * sizeof(Chi2Pair),
+                                     cudaMemcpyHostToDevice, stream));
             ctx->chi2_leaves_k = k;
-            ctx->chi2_n_leaves = (int)lv.size();
+            ctx->chi2_n_leaves = plan.n_leaves;
+            ctx->chi2_n_inner = plan.n_inner;
+            static_assert(sizeof(ctx->chi2_levels) == sizeof(Chi2Levels), "Chi2Levels mirror");
+            static_assert(sizeof(Chi2Pair) == sizeof(int2), "Chi2Pair mirrors int2");
+            memcpy(ctx->chi2_levels, &plan.levels, sizeof(Chi2Levels));
         }
-        const size_t smem = (size_t)ctx->chi2_n_leaves * sizeof(double);
+        Chi2Levels lv;
+        memcpy(&lv, ctx->chi2_levels, sizeof(lv));
+        const size_t smem = (size_t)(ctx->chi2_n_leaves + ctx->chi2_n_inner) * sizeof(double);
         static std::atomic<bool> configured[64];
         if (smem > 48 * 1024 && !configured[ctx->device & 63].load()) {
-            SLM_CUDA(cudaFuncSetAttribute(chi2_scan_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SLM_CUDA(cudaFuncSetAttribute(chi2_scan_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             configured[ctx->device & 63].store(true);
         }
-        chi2_scan_wide_kernel<<<(unsigned)n_db, 128, smem, stream>>>(hq, db, n_db, k, reinterpret_cast<const int2 *>(ctx->chi2_leaves.p),
-                                                                    ctx->chi2_n_leaves, dist);
+        const int2 *table_dev = reinterpret_cast<const int2 *>(ctx->chi2_leaves.p);
+        chi2_scan_wide_kernel<<<(unsigned)n_db, 128, smem, stream>>>(hq, db, n_db, k, table_dev, ctx->chi2_n_leaves,
+                                                                    table_dev + ctx->chi2_n_leaves, lv, dist);
     } else {
-        chi2_scan_kernel<<<(unsigned)((n_db + 127) / 128), 128, (size_t)k * sizeof(int), stream>>>(hq, db, n_db, k, dist);
+        chi2_scan_kernel<<<(unsigned)((n_db + 15) / 16), 128, 0, stream>>>(hq, db, n_db, k, dist);
     }
     SLM_CUDA(cudaGetLastError());
     argmin_kernel<<<1, 1024, 0, stream>>>(dist, n_db, best_idx, best_val);

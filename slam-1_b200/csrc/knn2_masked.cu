@@ -110,8 +110,9 @@ int slm_masked_knn2(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32_t 
     ctx->last_variant = SLM_VARIANT_POPC;
     ctx->last_kernel = "knn2_masked_kernel";
     const long long q_blocks = (nq + kMaskQPB - 1) / kMaskQPB;
-    // enough (query block, train slice) pairs to fill every SM a few times over; a slice is at least 256 rows
-    long long slices = (4ll * ctx->sm_count + q_blocks - 1) / q_blocks;
+    // (query block, train slice) pairs: at most two full waves of the 2 resident blocks per SM (102 registers x 256 threads) --
+    // rounding the slice count UP left a third wave that was 13 % full on the 2000 x 20000 shape; a slice is at least 256 rows
+    long long slices = (4ll * ctx->sm_count) / q_blocks;
     const long long max_slices = (nt + 255) / 256;
     if (slices > max_slices) slices = max_slices;
     if (slices > 4096) slices = 4096;

@@ -41,7 +41,8 @@ struct slm_ctx {
     slm_buf io;        // device copies of host inputs / outputs (slm_knn2_host)
     slm_buf tickets;   // per-group atomic tickets of the frame kernel (zero between launches)
     slm_buf chi2_leaves;   // leaves of numpy's pairwise-sum tree for chi2_leaves_k words (wide chi-square scan, bow.cu)
-    int chi2_leaves_k = 0, chi2_n_leaves = 0;
+    int chi2_leaves_k = 0, chi2_n_leaves = 0, chi2_n_inner = 0;
+    int chi2_levels[26] = {};   // Chi2Levels of bow.cu (number of levels, first inner node of every level)
     // pinned staging for host results
     void *pin = nullptr;
     size_t pin_bytes = 0;
@@ -242,11 +243,10 @@ int slm_auto_knn2_keys(slm_ctx *ctx, const uint32_t *q, int64_t nq, const uint32
 int slm_batched_knn2_keys(slm_ctx *ctx, const uint32_t *desc, int64_t n_per_frame, const int32_t *pairs_dev,
                           int64_t n_pairs, uint64_t *keys_out, cudaStream_t stream, const slm_chain *chain = nullptr);
 
-// chi-square scan: up to this many words one thread scans one stored histogram (query histogram in shared memory; the
-// recursive pairwise sum is then at most 4 frames = 576 bytes deep); above, one block per stored histogram
-// (chi2_scan_wide_kernel).  Largest supported vocabulary: kChi2MaxWords.
-static constexpr int kChi2SmemWords = 1024;
-static constexpr int kChi2MaxWords = 1 << 20;
+// chi-square scan: up to this many words a stored histogram is ONE leaf of numpy's pairwise sum (an 8-lane group per stored
+// histogram); above, one block per stored histogram (chi2_scan_wide_kernel).  Largest supported vocabulary: kChi2MaxWords.
+static constexpr int kChi2LeafWords = 128;
+static constexpr int kChi2MaxWords = 1 << 19;      // leaf + inner-node sums of one stored histogram must fit shared memory
 // ---- bag-of-words follow-on (bow.cu) ------------------------------------------------------------------
 int slm_bow_hist_impl(slm_ctx *ctx, const int32_t *idx, int64_t n, int32_t idx_stride, int32_t n_words, int32_t *hist,
                       cudaStream_t stream);

@@ -124,7 +124,7 @@ class BoW:
         return self._db[: self._n].cpu().numpy().astype(np.int64)
 
     # -- bag_of_words.py:29-53 ------------------------------------------------------------------------
-    MAX_SCAN_WORDS = 1 << 20   # slm_chi2_scan's limit (include/slammatch.h); config 4's 65 536-word vocabulary is well inside
+    MAX_SCAN_WORDS = 1 << 19   # slm_chi2_scan's limit (include/slammatch.h); config 4's 65 536-word vocabulary is well inside
 
     def _scan(self, hist_dev, n_db: int):
         import torch

@@ -51,7 +51,7 @@ def test_chi2_scan_first_minimum_wins_and_sum_order_is_numpys():
     from slammatch import _lib
     ctx = _lib.context(0)
     rng = np.random.default_rng(9)
-    for k in (5, 8, 50, 129, 300, 1000):
+    for k in (5, 8, 9, 50, 127, 128, 129, 300, 1000):
         n_db = 700
         db = rng.integers(0, 40, (n_db, k)).astype(np.int32)
         db[500] = db[20]                                    # exact tie: argmin must report 20
@@ -69,10 +69,10 @@ def test_chi2_scan_first_minimum_wins_and_sum_order_is_numpys():
 
 @pytest.mark.gpu
 def test_chi2_scan_wide_vocabularies_are_bit_exact_too():
-    """Above 1024 words (config 4's vocabulary has 65 536) the scan takes one block per stored histogram: the leaves of
-    numpy's pairwise-sum tree in parallel, then the tree itself -- still every distance bit-identical with np.sum; k changes
-    between calls (the cached leaf table is rebuilt), odd sizes, and the sizes between 8192 and 12288 words at which the
-    first version of the scan (one thread per histogram, recursive sum) outgrew the per-thread stack."""
+    """Above 128 words (config 4's vocabulary has 65 536) the scan takes one block per stored histogram: the leaves of
+    numpy's pairwise-sum tree by 8-lane groups, then the tree itself -- still every distance bit-identical with np.sum; k
+    changes between calls (the cached leaf table is rebuilt), odd sizes, and the sizes between 8192 and 12288 words at which
+    the first version of the scan (one thread per histogram, recursive sum) outgrew the per-thread stack."""
     import torch
     from slammatch import _lib
     ctx = _lib.context(0)
@@ -91,7 +91,7 @@ def test_chi2_scan_wide_vocabularies_are_bit_exact_too():
         torch.cuda.synchronize()
         assert np.array_equal(dist.cpu().numpy(), want), k
         assert int(bi.item()) == int(np.argmin(want)) == 1 and float(bv.item()) == float(np.min(want))
-    assert ctx.lib.slm_chi2_scan(ctx.handle, hd.data_ptr(), dd.data_ptr(), 1, (1 << 20) + 1, dist.data_ptr(), bi.data_ptr(),
+    assert ctx.lib.slm_chi2_scan(ctx.handle, hd.data_ptr(), dd.data_ptr(), 1, (1 << 19) + 1, dist.data_ptr(), bi.data_ptr(),
                                  bv.data_ptr(), None) == -1
 
 
