@@ -41,6 +41,18 @@ __global__ void bow_hist_kernel(const int *idx, long long n, int idx_stride, int
 
 __device__ __forceinline__ double chi2_term(int x, int y)
 {
+    // numpy evaluates 2 * (x - y)**2 and max(1, x + y) in int64 and divides in float64.  Same values here, with the two cases
+    // that make up almost every term of a sparse histogram (config 4: 2000 descriptors over 65 536 words) taken out of the
+    // division: a zero numerator gives +0.0 and a denominator of 1 gives the numerator itself, both exactly what the IEEE
+    // division returns -- and a zero operand sent every call of the double-precision division down its slow path (ncu:
+    // 123 warp instructions per 32 terms, issue-bound).  Small counts use 32-bit arithmetic and conversions.
+    if (((x | y) >= 0) && x < 32768 && y < 32768) {
+        const int d = x - y;
+        const unsigned num = 2u * (unsigned)(d * d), den = (unsigned)(x + y);        // < 2^31, < 2^16
+        if (num == 0u) return 0.0;
+        if (den <= 1u) return (double)num;
+        return __ddiv_rn((double)num, (double)den);
+    }
     const long long d = (long long)x - (long long)y;
     const long long num = 2 * d * d;                 // exact in int64, like numpy's integer arithmetic
     const long long den = max(1ll, (long long)x + (long long)y);

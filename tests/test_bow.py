@@ -96,6 +96,32 @@ def test_chi2_scan_wide_vocabularies_are_bit_exact_too():
 
 
 @pytest.mark.gpu
+def test_chi2_term_count_ranges_zero_one_and_beyond_16_bits():
+    """The per-word term takes a short path for the counts a real histogram holds (zero numerator, denominator 0 or 1, counts
+    below 32768) and 64-bit arithmetic beyond; both must give numpy's int64 / float64 value bit for bit, on every scan kernel
+    (narrow: k <= 128, wide: one block per histogram)."""
+    import torch
+    from slammatch import _lib
+    ctx = _lib.context(0)
+    rng = np.random.default_rng(11)
+    pool = np.array([0, 0, 0, 1, 1, 2, 3, 7, 255, 32766, 32767, 32768, 32769, 40000, 65535, 65536, 100000, 1 << 20, 1 << 30],
+                    dtype=np.int32)
+    for k, n_db in ((7, 400), (128, 300), (129, 200), (1000, 64), (4099, 20)):
+        db = pool[rng.integers(0, len(pool), (n_db, k))]
+        h = pool[rng.integers(0, len(pool), k)]
+        db[n_db - 1] = db[2] = h                                # exact tie at distance 0: argmin must report 2
+        want = np.array([orc.np_chi2(h.astype(np.int64), r.astype(np.int64)) for r in db])
+        hd, dd = torch.from_numpy(h).cuda(), torch.from_numpy(db).cuda()
+        dist = torch.empty(n_db, dtype=torch.float64, device="cuda")
+        bi = torch.empty(1, dtype=torch.int32, device="cuda"); bv = torch.empty(1, dtype=torch.float64, device="cuda")
+        _lib.check(ctx.lib.slm_chi2_scan(ctx.handle, hd.data_ptr(), dd.data_ptr(), n_db, k, dist.data_ptr(),
+                                         bi.data_ptr(), bv.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(dist.cpu().numpy(), want), k
+        assert int(bi.item()) == 2 and float(bv.item()) == 0.0
+
+
+@pytest.mark.gpu
 def test_bow_predict_with_a_64k_word_vocabulary():
     """BoW.predict / predict_previous at config 4's vocabulary size (was rejected: > 12288 words)."""
     from slammatch.bow import BoW
