@@ -69,20 +69,46 @@ __device__ __forceinline__ double chi2_term(int x, int y)
 // of 32 scattered words (one thread per stored histogram -- the first version of this scan -- reached 4 % of the HBM
 // bandwidth and needed device recursion); the three XOR-shuffle additions reproduce the association above exactly
 // (IEEE addition is commutative, so lane 1's r1 + r0 is lane 0's r0 + r1).  The result is valid in every lane of the group.
+// Memory-level parallelism: a leaf is at most 128 words = 16 steps of a group, and ALL of a leaf's loads are issued before the
+// first term is evaluated (the first form of this loop loaded, divided and added step by step: one 32-byte sector in flight per
+// group, 0.16-0.22 of the HBM bandwidth however sparse the histograms were).  Steps past the end of the leaf load nothing
+// and add nothing; every accumulator starts at +0.0 instead of at its first term, which is the same value bit for bit
+// (+0.0 + t = t for every t >= +0.0).
+constexpr int kChi2LeafSteps = 16;                       // kChi2LeafWords / 8
+
 __device__ __forceinline__ double chi2_leaf8(const int *hq, const int *row, int n, int j, unsigned group_mask)
 {
     double r = 0.0;
-    if (n < 8) {
-        for (int i = 0; i < n; ++i) r = __dadd_rn(r, chi2_term(__ldg(hq + i), __ldg(row + i)));
-        return r;
+    const int steps = n >> 3;                            // full steps of the eight accumulators (0 when n < 8)
+    if (steps > 0) {
+        int x[kChi2LeafSteps], y[kChi2LeafSteps];
+#pragma unroll
+        for (int s = 0; s < kChi2LeafSteps; ++s) {
+            const bool in = s < steps;
+            x[s] = in ? __ldg(hq + s * 8 + j) : 0;
+            y[s] = in ? __ldg(row + s * 8 + j) : 0;
+        }
+#pragma unroll
+        for (int s = 0; s < kChi2LeafSteps; ++s)
+            if (s < steps) r = __dadd_rn(r, chi2_term(x[s], y[s]));      // (+0.0 + first term = first term: numpy starts there)
+        r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 1));
+        r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 2));
+        r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 4));
     }
-    const int n8 = n - (n % 8);
-    r = chi2_term(__ldg(hq + j), __ldg(row + j));
-    for (int i = 8; i < n8; i += 8) r = __dadd_rn(r, chi2_term(__ldg(hq + i + j), __ldg(row + i + j)));
-    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 1));
-    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 2));
-    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 4));
-    for (int i = n8; i < n; ++i) r = __dadd_rn(r, chi2_term(__ldg(hq + i), __ldg(row + i)));
+    // the n % 8 trailing elements (all of them when n < 8) are added one by one, by every lane of the group
+    const int n8 = steps << 3;
+    if (n8 < n) {
+        int tx[7], ty[7];
+#pragma unroll
+        for (int b = 0; b < 7; ++b) {
+            const bool in = n8 + b < n;
+            tx[b] = in ? __ldg(hq + n8 + b) : 0;
+            ty[b] = in ? __ldg(row + n8 + b) : 0;
+        }
+#pragma unroll
+        for (int b = 0; b < 7; ++b)
+            if (n8 + b < n) r = __dadd_rn(r, chi2_term(tx[b], ty[b]));
+    }
     return r;
 }
 
