@@ -173,6 +173,20 @@ def cpu_matcher():
         return run, "port", "oracle/hamming_knn2.c (OpenMP)", orc.c_num_threads()
 
 
+def cpu_model() -> str:
+    """Host CPU model and logical core count (stated next to every CPU figure)."""
+    name = "unknown"
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.lower().startswith("model name"):
+                    name = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return f"{name}; os.cpu_count() = {os.cpu_count()}"
+
+
 def cpu_sample(w, cfg_id, target_s: float):
     """Pick a bounded sample of the workload that takes ~target_s on this host."""
     run, kind, desc, cores = cpu_matcher()
@@ -228,7 +242,7 @@ def reference_arm(args, w, cfg_id):
         "scaling": "strong" if w["sharded"] else "replicas", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "config": {"workload": w["name"], "sample": sample, "matcher": desc},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
-                         "single_thread": single},
+                         "single_thread": single, "cpu": cpu_model()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -652,7 +666,7 @@ def ours(args):
             dt = time.perf_counter() - t0
             cpu = {"value": qs.shape[0] * ts.shape[0] / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": f"{qs.shape[0]} queries x first {ts.shape[0]} train rows, one pass ({dt:.1f} s)",
-                   "matcher": desc}
+                   "matcher": desc, "cpu": cpu_model()}
         variant = head["variant"]
         line = {
             "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": head["steps"],
